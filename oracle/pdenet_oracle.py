@@ -1,0 +1,224 @@
+"""CPU oracle for the PDE-Net / PDE-Net 2.0 time-stepping hot path.
+
+*** TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED ***
+
+This file is the checker, never the product.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import it.  Nothing under ``pde-net_b200/`` imports it.
+
+Provenance.  The mounted reference (``/root/reference``) is the upstream
+``master`` branch: ``README.md`` (31 lines), ``.gitignore`` (1 line) and
+``figures/pdenet.jpg``.  It contains no source (README.md:8 points at the absent
+``PDE-Net`` / ``PDE-Net-2.0`` branches) and the numerical library it relies on,
+``ZichaoLong/aTEAM``, is un-vendored and un-pinned (``.gitignore:1``).  There are no
+reference tests, fixtures or golden vectors.  This oracle therefore *restates* the
+algorithm from the mathematics of the two papers named at README.md:5-6
+(arXiv 1710.09668, arXiv 1812.04426) in the op sequence the upstream code is
+built from -- wrap-around pad -> ``F.conv2d`` -> ``F.linear``/mul/cat -> Euler,
+with autograd for the reverse pass -- and is pinned by the known-answer tests in
+``tests/test_oracle_kat.py``.  Parity with the
+upstream code itself is **unpinned**.
+
+Each function cites the SURVEY.md section-8(a) row it restates; the upstream
+symbol names in those rows are recollections, not verifiable file:line anchors.
+
+Conventions fixed here (and mirrored by the CUDA path):
+  * state ``u``: ``[B, C, H, W]``, axis 0 of a filter acts along H, axis 1 along W;
+  * derivative order ``(o0, o1)``: ``o0`` along H (axis 0), ``o1`` along W (axis 1);
+  * filter bank order: total order ascending, then ``o0`` ascending:
+    ``(0,0), (0,1), (1,0), (0,2), (1,1), (2,0), ...``;
+  * feature index into SymNet: ``f = c * N + n`` (channel-major);
+  * SymNet flat layout per output channel: for i < L: ``W_i[2, m+i]`` row-major,
+    ``b_i[2]``; then ``w_f[m+L]``, ``b_f[1]``.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+__all__ = [
+    "order_list", "moment_axis_matrix", "m2k", "k2m", "initial_moments", "pinned_mask",
+    "filter_scales", "scaled_kernels", "periodic_pad", "fd2d_apply", "symnet_param_count",
+    "symnet_unpack", "symnet_apply", "right_hand_items", "step", "rollout",
+    "linear_step", "linear_rollout",
+]
+
+
+# ----------------------------------------------------------------------------- a1
+def moment_axis_matrix(k: int, dtype=torch.float64) -> torch.Tensor:
+    """SURVEY 8(a) row a1 (upstream ``MK.py::_MK.__init__``).
+
+    ``A[i, j] = (j - (k-1)//2)**i / i!`` for one axis of length ``k``.
+    """
+    c = (k - 1) // 2
+    A = torch.zeros(k, k, dtype=torch.float64)
+    for i in range(k):
+        for j in range(k):
+            A[i, j] = float((j - c) ** i) / math.factorial(i)
+    return A.to(dtype)
+
+
+# ----------------------------------------------------------------------------- a2
+def m2k(moment: torch.Tensor) -> torch.Tensor:
+    """Row a2 (``M2K.forward``): ``K = A0^-1 . M . A1^-T`` over leading dims."""
+    k0, k1 = moment.shape[-2:]
+    P0 = torch.linalg.inv(moment_axis_matrix(k0)).to(moment.dtype)
+    P1 = torch.linalg.inv(moment_axis_matrix(k1)).to(moment.dtype)
+    return P0 @ moment @ P1.transpose(0, 1)
+
+
+# ----------------------------------------------------------------------------- a3
+def k2m(kernel: torch.Tensor) -> torch.Tensor:
+    """Row a3 (``K2M.forward``): ``M = A0 . K . A1^T``; exact inverse of :func:`m2k`."""
+    k0, k1 = kernel.shape[-2:]
+    A0 = moment_axis_matrix(k0, kernel.dtype)
+    A1 = moment_axis_matrix(k1, kernel.dtype)
+    return A0 @ kernel @ A1.transpose(0, 1)
+
+
+# ----------------------------------------------------------------------------- a4
+def order_list(max_order: int) -> List[Tuple[int, int]]:
+    """Filter bank order: total order ascending, then order along H ascending."""
+    return [(j, o - j) for o in range(max_order + 1) for j in range(o + 1)]
+
+
+def initial_moments(k: int, orders: Sequence[Tuple[int, int]], dtype=torch.float64) -> torch.Tensor:
+    """Row a4: one-hot moment matrix at each filter's order."""
+    M = torch.zeros(len(orders), k, k, dtype=dtype)
+    for n, (o0, o1) in enumerate(orders):
+        M[n, o0, o1] = 1
+    return M
+
+
+def pinned_mask(k: int, order: Tuple[int, int], constraint="moment") -> torch.Tensor:
+    """Row a4 sum-rule constraint.  ``True`` where the moment entry is pinned.
+
+    ``'free'`` (or 0) pins nothing; ``'moment'`` is accuracy 1; an int ``acc`` pins all
+    entries of total order ``i + j < |order| + acc``; ``'frozen'`` pins everything.
+    """
+    mask = torch.zeros(k, k, dtype=torch.bool)
+    if constraint == "free" or constraint == 0:
+        return mask
+    if constraint == "frozen":
+        return ~mask
+    acc = 1 if constraint == "moment" else int(constraint)
+    s = order[0] + order[1] + acc
+    for i in range(k):
+        for j in range(k):
+            if i + j < s:
+                mask[i, j] = True
+    return mask
+
+
+def filter_scales(orders: Sequence[Tuple[int, int]], dx, dtype=torch.float64) -> torch.Tensor:
+    """Row a4: ``scale_n = 1 / (dx0**o0 * dx1**o1)``."""
+    dx0, dx1 = (dx, dx) if not isinstance(dx, (tuple, list)) else dx
+    return torch.tensor([1.0 / (dx0 ** o0 * dx1 ** o1) for (o0, o1) in orders], dtype=dtype)
+
+
+def scaled_kernels(moments: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    """``Ks[n] = scale_n * M2K(moment_n)`` -- what the stencil actually applies."""
+    return m2k(moments) * scales.to(moments.dtype)[:, None, None]
+
+
+# ----------------------------------------------------------------------------- a5
+def periodic_pad(u: torch.Tensor, k: int) -> torch.Tensor:
+    """Row a5 (``periodicpad``): wrap-around pad ``(r, k-1-r)`` on both spatial axes."""
+    r0, r1 = (k - 1) // 2, k - 1 - (k - 1) // 2
+    H, W = u.shape[-2:]
+    iy = torch.arange(-r0, H + r1) % H
+    ix = torch.arange(-r0, W + r1) % W
+    return u[..., iy, :][..., ix]
+
+
+# ----------------------------------------------------------------------------- a6
+def fd2d_apply(u: torch.Tensor, Ks: torch.Tensor) -> torch.Tensor:
+    """Row a6 (``_FDNd.forward``): cross-correlate every channel with every filter.
+
+    ``u [B,C,H,W]``, ``Ks [N,k,k]`` -> ``[B, C*N, H, W]`` with feature ``c*N + n``.
+    PyTorch ``conv2d`` semantics: no kernel flip.
+    """
+    B, C, H, W = u.shape
+    N, k, _ = Ks.shape
+    up = periodic_pad(u.reshape(B * C, 1, H, W), k)
+    d = F.conv2d(up, Ks[:, None])
+    return d.reshape(B, C * N, H, W)
+
+
+# ----------------------------------------------------------------------------- a7
+def symnet_param_count(m: int, L: int) -> int:
+    return sum(2 * (m + i) + 2 for i in range(L)) + (m + L) + 1
+
+
+def symnet_unpack(flat: torch.Tensor, m: int, L: int):
+    """Split one channel's flat parameter vector into ``[(W_i, b_i)...], (w_f, b_f)``."""
+    out, o = [], 0
+    for i in range(L):
+        W = flat[o:o + 2 * (m + i)].reshape(2, m + i); o += 2 * (m + i)
+        b = flat[o:o + 2]; o += 2
+        out.append((W, b))
+    wf = flat[o:o + m + L]; o += m + L
+    bf = flat[o:o + 1]; o += 1
+    assert o == flat.numel()
+    return out, (wf, bf)
+
+
+def symnet_apply(feat: torch.Tensor, flat: torch.Tensor, L: int) -> torch.Tensor:
+    """Row a7 (``expr.poly.forward``): ``feat [..., m]`` -> ``[...]``."""
+    m = feat.shape[-1]
+    hidden, (wf, bf) = symnet_unpack(flat, m, L)
+    h = feat
+    for (W, b) in hidden:
+        o = F.linear(h, W, b)
+        h = torch.cat([h, o[..., :1] * o[..., 1:]], dim=-1)
+    return F.linear(h, wf[None], bf)[..., 0]
+
+
+# ----------------------------------------------------------------------------- a8
+def right_hand_items(u: torch.Tensor, Ks: torch.Tensor, symnet: torch.Tensor, L: int) -> torch.Tensor:
+    """Row a8: ``F[b,c,y,x] = SymNet_c(all derivative features at (y,x))``.
+
+    ``symnet`` is ``[C, P]`` (one flat parameter vector per output channel).
+    """
+    d = fd2d_apply(u, Ks).permute(0, 2, 3, 1)  # channels-last features
+    return torch.stack([symnet_apply(d, symnet[c], L) for c in range(u.shape[1])], dim=1)
+
+
+# ----------------------------------------------------------------------------- a9
+def step(u, Ks, symnet, L, dt):
+    """Row a9 (``predict``): forward Euler ``u + dt * F(u)``."""
+    return u + dt * right_hand_items(u, Ks, symnet, L)
+
+
+# ----------------------------------------------------------------------------- a10
+def rollout(u0, Ks, symnet, L, dt, steps: int):
+    """Row a10 (``multistep``): list ``[u_1, ..., u_steps]``."""
+    states, u = [], u0
+    for _ in range(steps):
+        u = step(u, Ks, symnet, L, dt)
+        states.append(u)
+    return states
+
+
+# ----------------------------------------------------------------------------- a12
+def linear_step(u, K0, Ks, coe, dt):
+    """Row a12 (PDE-Net 1 ``VariantCoeLinear2d``): ``D0*u + dt * sum_n c_n . (D_n*u)``.
+
+    ``u [B,H,W]``, ``K0 [k,k]`` (learnable order-(0,0) filter), ``Ks [N,k,k]``,
+    ``coe [N,H,W]``.
+    """
+    B, H, W = u.shape
+    allK = torch.cat([K0[None], Ks], dim=0)
+    d = fd2d_apply(u[:, None], allK)  # [B, 1+N, H, W]
+    return d[:, 0] + dt * (coe[None] * d[:, 1:]).sum(dim=1)
+
+
+def linear_rollout(u0, K0, Ks, coe, dt, steps: int):
+    states, u = [], u0
+    for _ in range(steps):
+        u = linear_step(u, K0, Ks, coe, dt)
+        states.append(u)
+    return states

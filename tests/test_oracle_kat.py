@@ -1,0 +1,203 @@
+"""Known-answer tests that pin the oracle.
+
+The reference mount has no tests or golden vectors, so these are the pins.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdenet_oracle as O
+from oracle import pdenet_oracle_np as ONP
+
+torch.set_default_dtype(torch.float64)
+
+
+def onehot(k, i, j):
+    M = torch.zeros(k, k)
+    M[i, j] = 1
+    return M
+
+
+# KAT-1 ------------------------------------------------------------------
+@pytest.mark.parametrize("k,row", [
+    (3, [-1 / 2, 0, 1 / 2]),
+    (5, [1 / 12, -2 / 3, 0, 2 / 3, -1 / 12]),
+    (7, [-1 / 60, 3 / 20, -3 / 4, 0, 3 / 4, -3 / 20, 1 / 60]),
+])
+def test_kat1_first_derivative_rows(k, row):
+    K = O.m2k(onehot(k, 0, 1))
+    c = (k - 1) // 2
+    assert torch.allclose(K[c], torch.tensor(row), atol=1e-13)
+    # all other rows vanish: the (0,1) filter is a pure d/dx1 stencil
+    K[c] = 0
+    assert K.abs().max() < 1e-13
+    # and the transposed one-hot differentiates along axis 0
+    Kt = O.m2k(onehot(k, 1, 0))
+    assert torch.allclose(Kt[:, c], torch.tensor(row), atol=1e-13)
+
+
+def test_kat1_second_derivative_k3():
+    K = O.m2k(onehot(3, 0, 2))
+    assert torch.allclose(K[1], torch.tensor([1.0, -2.0, 1.0]), atol=1e-13)
+
+
+# KAT-2 ------------------------------------------------------------------
+@pytest.mark.parametrize("k,cond", [(3, 4.74), (5, 32.7), (7, 293.8)])
+def test_kat2_roundtrip_and_condition(k, cond):
+    g = torch.Generator().manual_seed(k)
+    M = torch.randn(4, k, k, generator=g)
+    assert torch.allclose(O.k2m(O.m2k(M)), M, atol=1e-9)
+    assert torch.allclose(O.m2k(O.k2m(M)), M, atol=1e-9)
+    A = O.moment_axis_matrix(k)
+    assert abs(torch.linalg.cond(A).item() - cond) / cond < 0.01
+
+
+# KAT-3 ------------------------------------------------------------------
+@pytest.mark.parametrize("k,tol", [
+    (5, {"01": 5.2e-7, "02": 1.7e-7, "11": 1.8e-5}),
+    (7, {"01": 4.4e-10, "02": 1.1e-10, "11": 5.7e-8}),
+])
+def test_kat3_truncation_error(k, tol):
+    n = 100
+    dx = 2 * math.pi / n
+    y, x = torch.meshgrid(torch.arange(n) * dx, torch.arange(n) * dx, indexing="ij")
+    # axis 1 (W) carries sin, axis 0 (H) carries cos 2y
+    u = (torch.sin(x) * torch.cos(2 * y))[None, None]
+    orders = [(0, 1), (0, 2), (1, 1)]
+    Ks = O.scaled_kernels(O.initial_moments(k, orders), O.filter_scales(orders, dx))
+    d = O.fd2d_apply(u, Ks)[0]
+    exact = [torch.cos(x) * torch.cos(2 * y), -torch.sin(x) * torch.cos(2 * y),
+             -2 * torch.cos(x) * torch.sin(2 * y)]
+    for name, dn, ex in zip(["01", "02", "11"], d, exact):
+        err = (dn - ex).abs().max().item()
+        assert err < 1.5 * tol[name], (name, err)
+        assert err > 0.3 * tol[name], (name, err)  # the KAT value, not merely a bound
+
+
+# KAT-4 ------------------------------------------------------------------
+def burgers_symnet(nu, N=6, C=2, L=2):
+    """Hand-set SymNet weights: channel 0 -> -u u_x - v u_y + nu lap u, channel 1 likewise.
+
+    Feature index f = c*N + n with orders (0,0),(0,1),(1,0),(0,2),(1,1),(2,0);
+    (0,1) is d/dx (axis W), (1,0) is d/dy (axis H).
+    """
+    m = C * N
+    P = O.symnet_param_count(m, L)
+    sym = torch.zeros(C, P)
+    iu, iv = 0, N
+    for c in range(C):
+        base = c * N
+        W0 = torch.zeros(2, m); b0 = torch.zeros(2)
+        W0[0, iu] = 1; W0[1, base + 1] = 1        # p0 = u,  q0 = w_x
+        W1 = torch.zeros(2, m + 1); b1 = torch.zeros(2)
+        W1[0, iv] = 1; W1[1, base + 2] = 1        # p1 = v,  q1 = w_y
+        wf = torch.zeros(m + L)
+        wf[m] = -1; wf[m + 1] = -1
+        wf[base + 3] = nu; wf[base + 5] = nu
+        sym[c] = torch.cat([W0.flatten(), b0, W1.flatten(), b1, wf, torch.zeros(1)])
+    return sym
+
+
+def test_kat4_burgers_step_matches_independent_numpy():
+    n, dt, nu = 32, 1e-3, 0.05
+    dx = 2 * math.pi / n
+    g = torch.Generator().manual_seed(0)
+    u0 = torch.randn(1, 2, n, n, generator=g)
+    orders = O.order_list(2)
+    Ks = O.scaled_kernels(O.initial_moments(3, orders), O.filter_scales(orders, dx))
+    sym = burgers_symnet(nu)
+    out = O.step(u0, Ks, sym, 2, dt)
+    un, vn = ONP.burgers_central_step(u0[0, 0].numpy(), u0[0, 1].numpy(), nu, dt, dx)
+    assert np.abs(out[0, 0].numpy() - un).max() < 1e-13 * max(1.0, np.abs(un).max()) * 10
+    assert np.abs(out[0, 1].numpy() - vn).max() < 1e-13 * max(1.0, np.abs(vn).max()) * 10
+
+
+# KAT-5 ------------------------------------------------------------------
+def random_model(k=5, P=2, C=2, L=2, dx=0.1, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(P)
+    M = O.initial_moments(k, orders) + 1e-2 * torch.randn(len(orders), k, k, generator=g)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    sym = 0.1 * torch.randn(C, O.symnet_param_count(C * len(orders), L), generator=g)
+    return Ks, sym
+
+
+def test_kat5_shift_equivariance():
+    Ks, sym = random_model()
+    g = torch.Generator().manual_seed(5)
+    u = torch.randn(2, 2, 12, 10, generator=g)
+    a = O.step(torch.roll(u, (3, -2), (2, 3)), Ks, sym, 2, 1e-2)
+    b = torch.roll(O.step(u, Ks, sym, 2, 1e-2), (3, -2), (2, 3))
+    assert torch.equal(a, b) or (a - b).abs().max() < 1e-14
+
+
+# KAT-6 ------------------------------------------------------------------
+@pytest.mark.parametrize("k", [3, 5])
+def test_kat6_gradcheck(k):
+    Ks, sym = random_model(k=k, dx=0.5, seed=k)
+    g = torch.Generator().manual_seed(6)
+    u = torch.randn(1, 2, 8, 8, generator=g, requires_grad=True)
+    Ks = Ks.clone().requires_grad_(True)
+    sym = sym.clone().requires_grad_(True)
+
+    def f(u, Ks, sym):
+        return O.rollout(u, Ks, sym, 2, 1e-2, 2)[-1]
+
+    assert torch.autograd.gradcheck(f, (u, Ks, sym), eps=1e-6, atol=1e-6, rtol=1e-5)
+
+
+# KAT-7 ------------------------------------------------------------------
+@pytest.mark.parametrize("order", [(0, 0), (0, 1), (1, 1), (2, 0)])
+def test_kat7_constraint_masks(order):
+    k = 7
+    s = order[0] + order[1]
+    mask = O.pinned_mask(k, order, "moment")
+    assert int(mask.sum()) == (s + 1) * (s + 2) // 2
+    assert int(O.pinned_mask(k, order, "free").sum()) == 0
+    assert int(O.pinned_mask(k, order, "frozen").sum()) == k * k
+    assert int(O.pinned_mask(k, order, 2).sum()) == (s + 2) * (s + 3) // 2
+    assert mask[order]  # the one-hot entry itself is pinned
+
+
+# cross-pin: torch autograd oracle == independent numpy adjoint -------------
+@pytest.mark.parametrize("k,L,C", [(3, 2, 2), (5, 2, 2), (7, 1, 1), (5, 3, 2)])
+def test_torch_oracle_matches_numpy_adjoint(k, L, C):
+    P = 2
+    Ks, sym = random_model(k=k, P=P, C=C, L=L, dx=0.3, seed=11 + k)
+    g = torch.Generator().manual_seed(1)
+    u0 = torch.randn(2, C, 9, 11, generator=g)
+    steps, dt = 3, 1e-2
+    u0t = u0.clone().requires_grad_(True)
+    Kst = Ks.clone().requires_grad_(True)
+    symt = sym.clone().requires_grad_(True)
+    states = O.rollout(u0t, Kst, symt, L, dt, steps)
+    w = torch.randn(states[-1].shape, generator=g)
+    (states[-1] * w).sum().backward()
+    st_np, lam0, dKs, dsym = ONP.rollout_fwd_bwd(u0.numpy(), Ks.numpy(), sym.numpy(), L, dt, steps, w.numpy())
+
+    def rel(a, b):
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+    for t in range(steps):
+        assert rel(st_np[t], states[t].detach().numpy()) < 1e-12
+    assert rel(lam0, u0t.grad.numpy()) < 1e-11
+    assert rel(dKs, Kst.grad.numpy()) < 1e-11
+    assert rel(dsym, symt.grad.numpy()) < 1e-11
+
+
+def test_linear_step_matches_manual():
+    k, N, H, W = 5, 15, 10, 12
+    g = torch.Generator().manual_seed(3)
+    orders = O.order_list(4)
+    assert len(orders) == N
+    M = O.initial_moments(k, orders) + 1e-2 * torch.randn(N, k, k, generator=g)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, 0.2))
+    K0 = O.m2k(onehot(k, 0, 0) + 1e-2 * torch.randn(k, k, generator=g))
+    coe = torch.randn(N, H, W, generator=g)
+    u = torch.randn(3, H, W, generator=g)
+    out = O.linear_step(u, K0, Ks, coe, 1.5e-2)
+    d = ONP.fd2d_apply(u[:, None].numpy(), torch.cat([K0[None], Ks]).numpy())
+    ref = d[:, 0] + 1.5e-2 * (coe.numpy()[None] * d[:, 1:]).sum(1)
+    assert np.abs(out.numpy() - ref).max() < 1e-11
