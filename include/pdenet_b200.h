@@ -1,0 +1,158 @@
+/*
+ * pdenet_b200.h -- C-ABI of the B200-native PDE-Net / PDE-Net 2.0 time-stepping hot path.
+ *
+ * Reference interfaces replaced.  The mounted reference (/root/reference) is the upstream
+ * `master` branch and contains no source (README.md:8 points at the absent `PDE-Net` /
+ * `PDE-Net-2.0` branches; the numerical library aTEAM is un-vendored, .gitignore:1), so no
+ * file:line anchor exists for the model code.  Each entry below therefore names the SURVEY.md
+ * section-8(a) row (and the upstream symbol recalled there) it stands in for; the only in-mount
+ * anchors are README.md:5-8 and figures/pdenet.jpg (the delta-t block chain).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer to contiguous row-major memory unless the
+ *     parameter name ends in `_host`;
+ *   - state u: [B, C, H, W]; axis 0 of a filter acts along H, axis 1 along W;
+ *   - filter bank: [N, k, k] cross-correlation kernels (PyTorch conv2d semantics, no flip),
+ *     already multiplied by 1/dx^|order| ("scaled kernels");
+ *   - feature index fed to SymNet: f = c*N + n;
+ *   - SymNet flat layout per output channel (Psym scalars): for i < L: W_i[2, m+i] row-major,
+ *     b_i[2]; then w_f[m+L], b_f[1];  m = C*N;
+ *   - the callee allocates nothing and keeps no global state; all work is ordered on `stream`
+ *     (a cudaStream_t passed as void*); reductions are deterministic (fixed order);
+ *   - return value 0 = success, negative = PDENET_E_* below.  No exceptions cross the boundary.
+ */
+#ifndef PDENET_B200_H_
+#define PDENET_B200_H_
+
+#include <stddef.h>
+
+#if defined(__GNUC__)
+#define PDENET_API __attribute__((visibility("default")))
+#else
+#define PDENET_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDENET_OK 0
+#define PDENET_E_BADARG (-1)      /* null pointer / non-positive size / even k            */
+#define PDENET_E_UNSUPPORTED (-2) /* (k, N, C, L) outside the compiled set                 */
+#define PDENET_E_WORKSPACE (-3)   /* workspace too small                                   */
+#define PDENET_E_CUDA (-4)        /* a CUDA runtime call / launch failed (see last error)  */
+
+#define PDENET_MAX_K 7
+#define PDENET_MAX_FILTERS 16
+#define PDENET_MAX_LAYERS 8
+
+/* gradient seed layout for the reverse rollout */
+#define PDENET_GRAD_LAST 0 /* grad_states is [B,C,H,W]: dLoss/d(state after the last step) */
+#define PDENET_GRAD_ALL 1  /* grad_states is [steps,B,C,H,W]: one seed per step            */
+
+PDENET_API int pdenet_version(void);
+PDENET_API const char *pdenet_error_string(int code);
+/* 1 if rollout kernels were compiled for (elem_size 4|8, k, N, C); L only needs L<=MAX_LAYERS */
+PDENET_API int pdenet_supported(int elem_size, int k, int N, int C, int L);
+/* number of SymNet scalars per output channel: sum_{i<L}(2(m+i)+2) + (m+L) + 1 */
+PDENET_API int pdenet_symnet_param_count(int m, int L);
+
+/* ---- rows a1-a3: moment <-> kernel map (upstream aTEAM MK.py::_MK/M2K/K2M) -----------------
+ * kernels[n] = scale[n] * A^-1 . moments[n] . A^-T,  A[i,j] = (j-(k-1)/2)^i / i!.
+ * scale_host: N host scalars (NULL = all ones).  k2m is the exact inverse (divides by scale).
+ * m2k_bwd maps dLoss/dkernels to dLoss/dmoments: scale * A^-T . dK . A^-1.
+ * pinned_mask (device, N*k*k bytes, may be NULL): entries with mask!=0 get gradient 0
+ * (row a4 `grad_proj`). */
+PDENET_API int pdenet_m2k_f64(const double *moments, const double *scale_host, double *kernels, int N, int k, void *stream);
+PDENET_API int pdenet_m2k_f32(const float *moments, const double *scale_host, float *kernels, int N, int k, void *stream);
+PDENET_API int pdenet_k2m_f64(const double *kernels, const double *scale_host, double *moments, int N, int k, void *stream);
+PDENET_API int pdenet_k2m_f32(const float *kernels, const double *scale_host, float *moments, int N, int k, void *stream);
+PDENET_API int pdenet_m2k_bwd_f64(const double *grad_kernels, const double *scale_host, const unsigned char *pinned_mask,
+                       double *grad_moments, int N, int k, void *stream);
+PDENET_API int pdenet_m2k_bwd_f32(const float *grad_kernels, const double *scale_host, const unsigned char *pinned_mask,
+                       float *grad_moments, int N, int k, void *stream);
+
+/* ---- rows a5-a6: periodic FD2d bank (upstream aTEAM FD.py::FD2d.forward + periodicpad) -----
+ * feats[b, c*N+n, y, x] = sum_{a,b'} kernels[n,a,b'] * u[b,c,(y+a-r)%H,(x+b'-r)%W]. */
+PDENET_API int pdenet_fd2d_fwd_f64(const double *u, const double *kernels, double *feats, int B, int C, int H, int W, int k,
+                        int N, void *stream);
+PDENET_API int pdenet_fd2d_fwd_f32(const float *u, const float *kernels, float *feats, int B, int C, int H, int W, int k,
+                        int N, void *stream);
+
+/* Reverse of the bank: grad_u[b,c] = sum_n corr^T(kernels[n], grad_feats[b,c*N+n]) (may be NULL),
+ * grad_kernels[n,a,b'] = sum_{b,c,y,x} grad_feats[b,c*N+n,y,x] * u[b,c,y+a-r,x+b'-r] (may be NULL).
+ * Workspace: pdenet_fd2d_bwd_workspace_bytes(k, N) bytes. */
+PDENET_API size_t pdenet_fd2d_bwd_workspace_bytes(int k, int N);
+PDENET_API int pdenet_fd2d_bwd_f64(const double *u, const double *grad_feats, const double *kernels, double *grad_u,
+                        double *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                        int k, int N, void *stream);
+PDENET_API int pdenet_fd2d_bwd_f32(const float *u, const float *grad_feats, const float *kernels, float *grad_u,
+                        float *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                        int k, int N, void *stream);
+
+/* ---- rows a7-a10: fused rollout (upstream polypde.py::POLYPDE2D.multistep) -----------------
+ * states[t] = state after step t+1, t = 0..steps-1;  u_{t+1} = u_t + dt * SymNet(FD2d(u_t)).
+ * One fused kernel per step: stencils + SymNet + Euler, tile+halo staged in shared memory. */
+PDENET_API int pdenet_rollout_fwd_f64(const double *u0, const double *kernels, const double *symnet, double *states, int B,
+                           int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API int pdenet_rollout_fwd_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B, int C,
+                           int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+
+/* ---- row a11: reverse rollout -------------------------------------------------------------
+ * Recomputes stencils + SymNet from the stored states; returns dLoss/du0 [B,C,H,W] (may be
+ * NULL), dLoss/dkernels [N,k,k] (w.r.t. the SCALED kernels; may be NULL = frozen filters) and
+ * dLoss/dsymnet [C,Psym] (may be NULL).  Outputs are overwritten, not accumulated.
+ * Workspace: at least pdenet_rollout_bwd_workspace_bytes(...) bytes of device memory
+ * (`batch_chunk` = how many trajectories share the derivative-adjoint scratch; 0 = all B). */
+PDENET_API size_t pdenet_rollout_bwd_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
+                                          int batch_chunk);
+PDENET_API int pdenet_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                           const double *kernels, const double *symnet, double *grad_u0, double *grad_kernels,
+                           double *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                           int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API int pdenet_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                           const float *kernels, const float *symnet, float *grad_u0, float *grad_kernels,
+                           float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                           int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+
+/* ---- row a12: PDE-Net 1 linear variable-coefficient rollout (VariantCoeLinear2d.forward) ----
+ * u_{t+1} = K0 (*) u_t + dt * sum_n coe[n,y,x] * (kernels[n] (*) u_t);  u: [B,H,W],
+ * coe: [N,H,W], id_kernel K0: [k,k].  grad_coe is [N,H,W]. */
+PDENET_API int pdenet_linear_rollout_fwd_f64(const double *u0, const double *id_kernel, const double *kernels,
+                                  const double *coe, double *states, int B, int H, int W, int k, int N, int steps,
+                                  double dt, void *stream);
+PDENET_API int pdenet_linear_rollout_fwd_f32(const float *u0, const float *id_kernel, const float *kernels, const float *coe,
+                                  float *states, int B, int H, int W, int k, int N, int steps, double dt,
+                                  void *stream);
+PDENET_API size_t pdenet_linear_rollout_bwd_workspace_bytes(int elem_size, int B, int H, int W, int k, int N);
+PDENET_API int pdenet_linear_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                                  const double *id_kernel, const double *kernels, const double *coe,
+                                  double *grad_u0, double *grad_id_kernel, double *grad_kernels, double *grad_coe,
+                                  void *workspace, size_t workspace_bytes, int B, int H, int W, int k, int N,
+                                  int steps, double dt, void *stream);
+PDENET_API int pdenet_linear_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                                  const float *id_kernel, const float *kernels, const float *coe, float *grad_u0,
+                                  float *grad_id_kernel, float *grad_kernels, float *grad_coe, void *workspace,
+                                  size_t workspace_bytes, int B, int H, int W, int k, int N, int steps, double dt,
+                                  void *stream);
+
+/* ---- slab domain decomposition helpers (config 5) --------------------------------
+ * Same step as the rollout, but on a slab of rows that is NOT periodic along H: the caller
+ * supplies the slab with `halo` ghost rows above and below already filled (by the NVLink halo
+ * exchange): u_ext is [B, C, Hs + 2*halo, W]; out is [B, C, Hs, W] written at out_row_stride
+ * rows per image so it can land inside another extended buffer. */
+PDENET_API int pdenet_slab_step_fwd_f64(const double *u_ext, const double *kernels, const double *symnet, double *out, int B,
+                             int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
+                             int N, int L, double dt, void *stream);
+PDENET_API int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const float *symnet, float *out, int B,
+                             int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
+                             int N, int L, double dt, void *stream);
+
+/* ---- measurement helper: register-only FMA loop, returns elapsed ms for `flops` flops -------
+ * (used by bench.py for the CUDA-core FLOP roofline denominator). */
+PDENET_API int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDENET_B200_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libpdenet_b200.so (the C-ABI declared in include/pdenet_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing (or a call returns a
+negative code) this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpdenet_b200.so")
+
+OK, E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
+GRAD_LAST, GRAD_ALL = 0, 1
+MAX_K, MAX_FILTERS, MAX_LAYERS = 7, 16, 8
+
+_vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); "{t}" expands to f64 / f32
+_PROTOS = {
+    "pdenet_version": (_i, []),
+    "pdenet_error_string": (C.c_char_p, [_i]),
+    "pdenet_supported": (_i, [_i] * 5),
+    "pdenet_symnet_param_count": (_i, [_i, _i]),
+    "pdenet_m2k_{t}": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "pdenet_k2m_{t}": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "pdenet_m2k_bwd_{t}": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "pdenet_fd2d_fwd_{t}": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
+    "pdenet_fd2d_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "pdenet_fd2d_bwd_{t}": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_vp]),
+    "pdenet_rollout_fwd_{t}": (_i, [_vp] * 4 + [_i] * 8 + [_d, _vp]),
+    "pdenet_rollout_bwd_workspace_bytes": (_sz, [_i] * 9),
+    "pdenet_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
+    "pdenet_linear_rollout_fwd_{t}": (_i, [_vp] * 5 + [_i] * 6 + [_d, _vp]),
+    "pdenet_linear_rollout_bwd_workspace_bytes": (_sz, [_i] * 6),
+    "pdenet_linear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 8 + [_sz] + [_i] * 6 + [_d, _vp]),
+    "pdenet_slab_step_fwd_{t}": (_i, [_vp] * 4 + [_i] * 10 + [_d, _vp]),
+    "pdenet_fma_peak": (_i, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float), _vp]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/pdenet_b200.h declares."""
+    out = []
+    for name in _PROTOS:
+        if "{t}" in name:
+            out += [name.format(t="f64"), name.format(t="f32")]
+        else:
+            out.append(name)
+    return out
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "pdenet_b200: %s is missing -- build it with `python pde-net_b200/build.py` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            for n in ([name.format(t="f64"), name.format(t="f32")] if "{t}" in name else [name]):
+                fn = getattr(l, n)
+                fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+class PdenetError(RuntimeError):
+    def __init__(self, code, what):
+        self.code = code
+        msg = lib().pdenet_error_string(code).decode()
+        super().__init__("%s failed: %s (code %d)" % (what, msg, code))
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise PdenetError(code, what)
+
+
+def fn(name: str, dtype) -> C._CFuncPtr:
+    """Typed entry point for a torch dtype: fn('pdenet_rollout_fwd', torch.float64)."""
+    import torch
+    if dtype == torch.float64:
+        return getattr(lib(), name + "_f64")
+    if dtype == torch.float32:
+        return getattr(lib(), name + "_f32")
+    raise TypeError("pdenet_b200 supports float64 and float32, got %s" % dtype)

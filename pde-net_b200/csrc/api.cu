@@ -1,0 +1,791 @@
+// C-ABI of the PDE-Net hot path (see include/pdenet_b200.h).  No torch types, no global state;
+// everything is ordered on the caller's stream.
+#include "../../include/pdenet_b200.h"
+#include "launch.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace pdenet {
+
+// ---------------------------------------------------------------------------------------------
+// extern templates: the heavy kernels live in inst_<type>_k<K>.o
+#define PDENET_EXTERN(TT, KK)                                                                                     \
+  extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
+  extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, cudaStream_t);                          \
+  extern template int adjoint_vlb<TT, KK>();                                                                     \
+  extern template void step_tile<TT, KK>(int &, int &);                                                          \
+  extern template void adjoint_tile<TT, KK>(int &, int &);
+PDENET_EXTERN(double, 3) PDENET_EXTERN(double, 5) PDENET_EXTERN(double, 7)
+PDENET_EXTERN(float, 3) PDENET_EXTERN(float, 5) PDENET_EXTERN(float, 7)
+#undef PDENET_EXTERN
+
+#define PDENET_DISPATCH_K(k, EXPR)                                                                                \
+  switch (k) {                                                                                                    \
+  case 3: {                                                                                                       \
+    constexpr int KK_ = 3;                                                                                        \
+    EXPR;                                                                                                         \
+  } break;                                                                                                        \
+  case 5: {                                                                                                       \
+    constexpr int KK_ = 5;                                                                                        \
+    EXPR;                                                                                                         \
+  } break;                                                                                                        \
+  case 7: {                                                                                                       \
+    constexpr int KK_ = 7;                                                                                        \
+    EXPR;                                                                                                         \
+  } break;                                                                                                        \
+  default:                                                                                                        \
+    return PDENET_E_UNSUPPORTED;                                                                                  \
+  }
+
+static int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+static int symnet_param_count(int m, int L) {
+  int s = 0;
+  for (int i = 0; i < L; ++i) s += 2 * (m + i) + 2;
+  return s + (m + L) + 1;
+}
+
+static bool nc_supported(int N, int C) {
+#define PDENET_CASE(NN, CC)                                                                                       \
+  if (N == NN && C == CC) return true;
+  PDENET_FOR_NC(PDENET_CASE)
+#undef PDENET_CASE
+  return false;
+}
+static bool lin_supported(int NF) {
+#define PDENET_CASE(NN)                                                                                           \
+  if (NF == NN) return true;
+  PDENET_FOR_LIN(PDENET_CASE)
+#undef PDENET_CASE
+  return false;
+}
+// vector length of the SymNet-gradient warp reduction: needs M + L + 1 <= VL
+static int pick_vl(int M, int L) {
+  if (M + L + 1 <= 16) return 16;
+  if (M + L + 1 <= 32) return 32;
+  return 0;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// moment <-> kernel map (rows a1-a3)
+struct Mat7 {
+  double m[PDENET_MAX_K * PDENET_MAX_K];
+};
+struct Scales {
+  double s[PDENET_MAX_FILTERS];
+};
+
+// A[i][j] = (j - c)^i / i!   (row a1)
+static void moment_matrix(int k, long double *A) {
+  const int c = (k - 1) / 2;
+  for (int i = 0; i < k; ++i) {
+    long double fact = 1;
+    for (int q = 2; q <= i; ++q) fact *= q;
+    for (int j = 0; j < k; ++j) A[i * k + j] = powl((long double)(j - c), (long double)i) / fact;
+  }
+}
+static void invert(int k, const long double *A, long double *Ai) {
+  long double a[PDENET_MAX_K][2 * PDENET_MAX_K];
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) {
+      a[i][j] = A[i * k + j];
+      a[i][k + j] = i == j ? 1.0L : 0.0L;
+    }
+  for (int col = 0; col < k; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < k; ++r)
+      if (fabsl(a[r][col]) > fabsl(a[piv][col])) piv = r;
+    if (piv != col)
+      for (int j = 0; j < 2 * k; ++j) {
+        long double t = a[col][j];
+        a[col][j] = a[piv][j];
+        a[piv][j] = t;
+      }
+    const long double d = a[col][col];
+    for (int j = 0; j < 2 * k; ++j) a[col][j] /= d;
+    for (int r = 0; r < k; ++r)
+      if (r != col) {
+        const long double f = a[r][col];
+        if (f != 0)
+          for (int j = 0; j < 2 * k; ++j) a[r][j] -= f * a[col][j];
+      }
+  }
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) Ai[i * k + j] = a[i][k + j];
+}
+
+// out[n][x][y] = s[n] * sum_{i,j} Q[x][i] * in[n][i][j] * Q[y][j], optionally masked
+template <typename T>
+__global__ void sandwich_kernel(const T *in, T *out, int k, Mat7 Q, Scales sc, const unsigned char *mask) {
+  __shared__ double tmp[PDENET_MAX_K * PDENET_MAX_K];
+  const int n = blockIdx.x, t = threadIdx.x, kk = k * k;
+  const int x = t / k, y = t % k;
+  if (t < kk) {
+    // tmp[x][j] = sum_i Q[x][i] in[i][j]   (here y plays j)
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += Q.m[x * k + i] * (double)in[n * kk + i * k + y];
+    tmp[t] = s;
+  }
+  __syncthreads();
+  if (t < kk) {
+    double s = 0.0;
+    for (int j = 0; j < k; ++j) s += tmp[x * k + j] * Q.m[y * k + j];
+    s *= sc.s[n];
+    if (mask && mask[n * kk + t]) s = 0.0;
+    out[n * kk + t] = (T)s;
+  }
+}
+
+enum { SW_M2K = 0, SW_K2M = 1, SW_M2K_BWD = 2 };
+
+template <typename T>
+static int sandwich(int which, const T *in, const double *scale_host, const unsigned char *mask, T *out, int N,
+                    int k, void *stream) {
+  if (!in || !out || N <= 0 || N > PDENET_MAX_FILTERS || k <= 0 || k > PDENET_MAX_K || (k % 2) == 0)
+    return PDENET_E_BADARG;
+  long double A[PDENET_MAX_K * PDENET_MAX_K], Ai[PDENET_MAX_K * PDENET_MAX_K];
+  moment_matrix(k, A);
+  invert(k, A, Ai);
+  Mat7 Q;
+  Scales sc;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) {
+      if (which == SW_M2K) Q.m[i * k + j] = (double)Ai[i * k + j];
+      if (which == SW_K2M) Q.m[i * k + j] = (double)A[i * k + j];
+      if (which == SW_M2K_BWD) Q.m[i * k + j] = (double)Ai[j * k + i];
+    }
+  for (int n = 0; n < N; ++n) {
+    const double s = scale_host ? scale_host[n] : 1.0;
+    sc.s[n] = which == SW_K2M ? 1.0 / s : s;
+  }
+  sandwich_kernel<T><<<N, 64, 0, (cudaStream_t)stream>>>(in, out, k, Q, sc, mask);
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+static bool bad_geom(int B, int C, int H, int W, int k, int N) {
+  return B <= 0 || C <= 0 || H <= 0 || W <= 0 || k <= 0 || (k % 2) == 0 || N <= 0;
+}
+
+template <typename T, int K>
+static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int H, int W, cudaStream_t st) {
+  int tw, th;
+  step_tile<T, K>(tw, th);
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
+  p.n_items = B * p.tiles_x * p.tiles_y;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  return launch_step<T, K>(mode, N, C, VL, p, grid, st);
+}
+
+template <typename T, int K>
+static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaStream_t st) {
+  int tw, th;
+  adjoint_tile<T, K>(tw, th);
+  p.B = B;
+  p.C = C;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
+  p.n_items = B * C * p.tiles_x * p.tiles_y;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  return launch_adjoint<T, K>(p, grid, st);
+}
+
+// ---- forward rollout (rows a5-a10) -----------------------------------------------------------
+template <typename T>
+static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states, int B, int C, int H, int W, int k,
+                       int N, int L, int steps, double dt, void *stream) {
+  if (!u0 || !kernels || !symnet || !states || bad_geom(B, C, H, W, k, N) || L < 0 || steps < 0)
+    return PDENET_E_BADARG;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  const size_t stride = (size_t)B * C * H * W;
+  StepParams<T> p;
+  memset(&p, 0, sizeof(p));
+  p.kernels = kernels;
+  p.symnet = symnet;
+  p.L = L;
+  p.Psym = symnet_param_count(C * N, L);
+  p.dt = (T)dt;
+  p.wrap_y = 1;
+  p.u_rows = p.out_rows = H;
+  for (int t = 0; t < steps; ++t) {
+    p.u = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
+    p.out = states + (size_t)t * stride;
+    int rc = 0;
+    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, H, W, (cudaStream_t)stream)));
+    if (rc) return rc;
+  }
+  return PDENET_OK;
+}
+
+template <typename T>
+static int fd2d_fwd(const T *u, const T *kernels, T *feats, int B, int C, int H, int W, int k, int N, void *stream) {
+  if (!u || !kernels || !feats || bad_geom(B, C, H, W, k, N)) return PDENET_E_BADARG;
+  if (!nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  StepParams<T> p;
+  memset(&p, 0, sizeof(p));
+  p.kernels = kernels;
+  p.symnet = kernels; // unused in MODE_FEATS (Psym = 0)
+  p.wrap_y = 1;
+  p.u_rows = p.out_rows = H;
+  p.u = u;
+  p.out = feats;
+  int rc = 0;
+  PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FEATS, N, C, 16, p, B, H, W, (cudaStream_t)stream)));
+  return rc;
+}
+
+template <typename T>
+static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u, T *grad_kernels, void *workspace,
+                    size_t ws_bytes, int B, int C, int H, int W, int k, int N, void *stream) {
+  if (!u || !grad_feats || !kernels || !workspace || bad_geom(B, C, H, W, k, N) || N > PDENET_MAX_FILTERS)
+    return PDENET_E_BADARG;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64), slots = sms * 8;
+  const size_t need = (size_t)slots * N * vlb * sizeof(double);
+  if (ws_bytes < need) return PDENET_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double *dkp = (double *)workspace;
+  if (grad_kernels && cudaMemsetAsync(dkp, 0, need, st) != cudaSuccess) return PDENET_E_CUDA;
+  AdjParams<T> q;
+  memset(&q, 0, sizeof(q));
+  q.g = grad_feats;
+  q.g_rows = H;
+  q.u = u;
+  q.u_rows = H;
+  q.wrap_y = 1;
+  q.lam_out = grad_u;
+  q.lo_rows = H;
+  q.kernels = kernels;
+  q.dk_partial = grad_kernels ? dkp : nullptr;
+  int rc = 0;
+  if (grad_u || grad_kernels) {
+    PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, C, N, H, W, st)));
+    if (rc) return rc;
+  }
+  if (grad_kernels) {
+    const int n = N * kk;
+    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
+  }
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+template <typename T>
+static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *out, int B, int C, int Hs, int W,
+                         int halo, int out_rows, int out_off, int k, int N, int L, double dt, void *stream) {
+  if (!u_ext || !kernels || !symnet || !out || bad_geom(B, C, Hs, W, k, N) || L < 0 || halo < (k - 1) / 2 ||
+      out_rows < Hs + out_off || out_off < 0)
+    return PDENET_E_BADARG;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  StepParams<T> p;
+  memset(&p, 0, sizeof(p));
+  p.kernels = kernels;
+  p.symnet = symnet;
+  p.L = L;
+  p.Psym = symnet_param_count(C * N, L);
+  p.dt = (T)dt;
+  p.wrap_y = 0;
+  p.u = u_ext;
+  p.u_rows = Hs + 2 * halo;
+  p.u_off = halo;
+  p.out = out;
+  p.out_rows = out_rows;
+  p.out_off = out_off;
+  int rc = 0;
+  PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, Hs, W, (cudaStream_t)stream)));
+  return rc;
+}
+
+// ---- reverse rollout (row a11) ---------------------------------------------------------------
+struct BwdLayout {
+  size_t off_g, off_lam0, off_lam1, off_dk, off_sym, total;
+  int chunk, dk_slots, sym_slots, vlb;
+};
+
+static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N, int L, int batch_chunk, int sms) {
+  BwdLayout l;
+  l.chunk = (batch_chunk <= 0 || batch_chunk > B) ? B : batch_chunk;
+  const int kk = k * k;
+  l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
+  l.dk_slots = sms * 8;
+  l.sym_slots = sms;
+  const size_t img = (size_t)H * W;
+  size_t o = 0;
+  l.off_g = o;
+  o = align_up(o + (size_t)l.chunk * C * N * img * es, 256);
+  l.off_lam0 = o;
+  o = align_up(o + (size_t)B * C * img * es, 256);
+  l.off_lam1 = o;
+  o = align_up(o + (size_t)B * C * img * es, 256);
+  l.off_dk = o;
+  o = align_up(o + (size_t)l.dk_slots * N * l.vlb * sizeof(double), 256);
+  l.off_sym = o;
+  o = align_up(o + (size_t)l.sym_slots * C * symnet_param_count(C * N, L) * sizeof(double), 256);
+  l.total = o;
+  return l;
+}
+
+template <typename T>
+static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int grad_mode, const T *kernels,
+                       const T *symnet, T *grad_u0, T *grad_kernels, T *grad_symnet, void *workspace,
+                       size_t ws_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
+                       double dt, void *stream) {
+  if (!u0 || !grad_states || !kernels || !symnet || !workspace || bad_geom(B, C, H, W, k, N) || L < 0 ||
+      steps < 1 || (steps > 1 && !states) || (grad_mode != PDENET_GRAD_LAST && grad_mode != PDENET_GRAD_ALL))
+    return PDENET_E_BADARG;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  const int M = C * N;
+  const int VL = pick_vl(M, L);
+  if (!VL) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const BwdLayout lay = bwd_layout(sizeof(T), B, C, H, W, k, N, L, batch_chunk, sms);
+  if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
+  char *ws = (char *)workspace;
+  T *gbuf = (T *)(ws + lay.off_g);
+  T *lamb[2] = {(T *)(ws + lay.off_lam0), (T *)(ws + lay.off_lam1)};
+  double *dkp = (double *)(ws + lay.off_dk);
+  double *symp = (double *)(ws + lay.off_sym);
+  const int Psym = symnet_param_count(M, L);
+  if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * N * lay.vlb * sizeof(double), st) != cudaSuccess ||
+      cudaMemsetAsync(symp, 0, (size_t)lay.sym_slots * C * Psym * sizeof(double), st) != cudaSuccess)
+    return PDENET_E_CUDA;
+
+  const size_t img = (size_t)H * W;
+  const size_t stride = (size_t)B * C * img;
+  const T *lam_in = grad_mode == PDENET_GRAD_ALL ? grad_states + (size_t)(steps - 1) * stride : grad_states;
+  int cur = 0;
+  for (int t = steps - 1; t >= 0; --t) {
+    const T *ut = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
+    T *lam_out = t == 0 ? grad_u0 : lamb[cur];
+    const T *inject = (grad_mode == PDENET_GRAD_ALL && t > 0) ? grad_states + (size_t)(t - 1) * stride : nullptr;
+    const bool need_b = lam_out != nullptr || grad_kernels != nullptr;
+    for (int b0 = 0; b0 < B; b0 += lay.chunk) {
+      const int nb = (B - b0) < lay.chunk ? (B - b0) : lay.chunk;
+      const size_t boff = (size_t)b0 * C * img;
+      StepParams<T> p;
+      memset(&p, 0, sizeof(p));
+      p.kernels = kernels;
+      p.symnet = symnet;
+      p.L = L;
+      p.Psym = Psym;
+      p.dt = (T)dt;
+      p.wrap_y = 1;
+      p.u = ut + boff;
+      p.u_rows = H;
+      p.lam = lam_in + boff;
+      p.lam_rows = H;
+      p.g = gbuf;
+      p.g_rows = H;
+      p.sym_partial = symp;
+      int rc = 0;
+      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
+      if (rc) return rc;
+      if (!need_b) continue;
+      AdjParams<T> q;
+      memset(&q, 0, sizeof(q));
+      q.g = gbuf;
+      q.g_rows = H;
+      q.u = ut + boff;
+      q.u_rows = H;
+      q.wrap_y = 1;
+      q.lam_in = lam_in + boff;
+      q.li_rows = H;
+      q.inject = inject ? inject + boff : nullptr;
+      q.inj_rows = H;
+      q.lam_out = lam_out ? lam_out + boff : nullptr;
+      q.lo_rows = H;
+      q.kernels = kernels;
+      q.dk_partial = grad_kernels ? dkp : nullptr;
+      PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, nb, C, N, H, W, st)));
+      if (rc) return rc;
+    }
+    lam_in = lam_out;
+    cur ^= 1;
+    if (!lam_out && t > 0) return PDENET_E_BADARG; // unreachable: lam_out is only NULL at t == 0
+  }
+  if (grad_kernels) {
+    const int n = N * k * k;
+    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
+  }
+  if (grad_symnet) {
+    const int n = C * Psym;
+    reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(symp, lay.sym_slots, n, grad_symnet);
+  }
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+// ---- PDE-Net 1 linear rollout (row a12) ------------------------------------------------------
+template <typename T>
+static int linear_fwd(const T *u0, const T *id_kernel, const T *kernels, const T *coe, T *states, int B, int H,
+                      int W, int k, int N, int steps, double dt, void *stream) {
+  if (!u0 || !id_kernel || !kernels || !coe || !states || bad_geom(B, 1, H, W, k, N) || steps < 0)
+    return PDENET_E_BADARG;
+  if (!lin_supported(N + 1)) return PDENET_E_UNSUPPORTED;
+  const size_t stride = (size_t)B * H * W;
+  StepParams<T> p;
+  memset(&p, 0, sizeof(p));
+  p.kernels = kernels;
+  p.kernels0 = id_kernel;
+  p.symnet = coe;
+  p.dt = (T)dt;
+  p.wrap_y = 1;
+  p.u_rows = p.out_rows = H;
+  for (int t = 0; t < steps; ++t) {
+    p.u = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
+    p.out = states + (size_t)t * stride;
+    int rc = 0;
+    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_LIN_FWD, N + 1, 1, 16, p, B, H, W, (cudaStream_t)stream)));
+    if (rc) return rc;
+  }
+  return PDENET_OK;
+}
+
+struct LinLayout {
+  size_t off_g, off_lam0, off_lam1, off_dk, off_dcoe, total;
+  int dk_slots, vlb;
+};
+static LinLayout lin_layout(size_t es, int B, int H, int W, int k, int N, int sms) {
+  LinLayout l;
+  const int kk = k * k;
+  l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
+  l.dk_slots = sms * 8;
+  const size_t img = (size_t)H * W;
+  size_t o = 0;
+  l.off_g = o;
+  o = align_up(o + (size_t)B * (N + 1) * img * es, 256);
+  l.off_lam0 = o;
+  o = align_up(o + (size_t)B * img * es, 256);
+  l.off_lam1 = o;
+  o = align_up(o + (size_t)B * img * es, 256);
+  l.off_dk = o;
+  o = align_up(o + (size_t)l.dk_slots * (N + 1) * l.vlb * sizeof(double), 256);
+  l.off_dcoe = o;
+  o = align_up(o + (size_t)B * N * img * es, 256);
+  l.total = o;
+  return l;
+}
+
+// grad_coe[n][pix] = sum_b partial[b][n][pix]  (fixed order)
+template <typename T> __global__ void reduce_dcoe_kernel(const T *partial, int B, size_t n, T *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T s = T(0);
+  for (int b = 0; b < B; ++b) s += partial[(size_t)b * n + i];
+  out[i] = s;
+}
+
+template <typename T>
+static int linear_bwd(const T *u0, const T *states, const T *grad_states, int grad_mode, const T *id_kernel,
+                      const T *kernels, const T *coe, T *grad_u0, T *grad_id_kernel, T *grad_kernels, T *grad_coe,
+                      void *workspace, size_t ws_bytes, int B, int H, int W, int k, int N, int steps, double dt,
+                      void *stream) {
+  if (!u0 || !grad_states || !id_kernel || !kernels || !coe || !workspace || bad_geom(B, 1, H, W, k, N) ||
+      steps < 1 || (steps > 1 && !states) || (grad_mode != PDENET_GRAD_LAST && grad_mode != PDENET_GRAD_ALL))
+    return PDENET_E_BADARG;
+  if (!lin_supported(N + 1)) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const LinLayout lay = lin_layout(sizeof(T), B, H, W, k, N, sms);
+  if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
+  char *ws = (char *)workspace;
+  T *gbuf = (T *)(ws + lay.off_g);
+  T *lamb[2] = {(T *)(ws + lay.off_lam0), (T *)(ws + lay.off_lam1)};
+  double *dkp = (double *)(ws + lay.off_dk);
+  T *dcoe = (T *)(ws + lay.off_dcoe);
+  const size_t img = (size_t)H * W;
+  const size_t stride = (size_t)B * img;
+  const bool want_dk = grad_id_kernel != nullptr || grad_kernels != nullptr;
+  if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * (N + 1) * lay.vlb * sizeof(double), st) != cudaSuccess ||
+      cudaMemsetAsync(dcoe, 0, (size_t)B * N * img * sizeof(T), st) != cudaSuccess)
+    return PDENET_E_CUDA;
+  const T *lam_in = grad_mode == PDENET_GRAD_ALL ? grad_states + (size_t)(steps - 1) * stride : grad_states;
+  int cur = 0;
+  for (int t = steps - 1; t >= 0; --t) {
+    const T *ut = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
+    T *lam_out = t == 0 ? grad_u0 : lamb[cur];
+    const T *inject = (grad_mode == PDENET_GRAD_ALL && t > 0) ? grad_states + (size_t)(t - 1) * stride : nullptr;
+    StepParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.kernels = kernels;
+    p.kernels0 = id_kernel;
+    p.symnet = coe;
+    p.dt = (T)dt;
+    p.wrap_y = 1;
+    p.u = ut;
+    p.u_rows = H;
+    p.lam = lam_in;
+    p.lam_rows = H;
+    p.g = gbuf;
+    p.g_rows = H;
+    p.dcoe_partial = dcoe;
+    int rc = 0;
+    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_LIN_BWD_A, N + 1, 1, 16, p, B, H, W, st)));
+    if (rc) return rc;
+    if (lam_out || want_dk) {
+      AdjParams<T> q;
+      memset(&q, 0, sizeof(q));
+      q.g = gbuf;
+      q.g_rows = H;
+      q.u = ut;
+      q.u_rows = H;
+      q.wrap_y = 1;
+      q.lam_in = nullptr; // the D0 filter carries the identity path
+      q.inject = inject;
+      q.inj_rows = H;
+      q.lam_out = lam_out;
+      q.lo_rows = H;
+      q.kernels = kernels;
+      q.kernels0 = id_kernel;
+      q.dk_partial = want_dk ? dkp : nullptr;
+      PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, 1, N + 1, H, W, st)));
+      if (rc) return rc;
+    }
+    lam_in = lam_out;
+    cur ^= 1;
+  }
+  const int kk = k * k;
+  if (grad_id_kernel)
+    reduce_dk_kernel<T><<<(kk + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
+  if (grad_kernels) {
+    // filters 1..N: same partial layout, shifted by one filter
+    const int n = N * kk;
+    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
+                                                         grad_kernels);
+  }
+  if (grad_coe) {
+    const size_t n = (size_t)N * img;
+    reduce_dcoe_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dcoe, B, n, grad_coe);
+  }
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+// ---- FMA peak microbenchmark -----------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b) {
+  T x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (T)(threadIdx.x + i) * (T)1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = fma_(x[i], a, b);
+  }
+  T s = T(0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == (T)123456789) out[0] = s; // never true; keeps the loop alive
+}
+
+} // namespace pdenet
+
+using namespace pdenet;
+
+extern "C" {
+
+int pdenet_version(void) { return 100; }
+
+const char *pdenet_error_string(int code) {
+  switch (code) {
+  case PDENET_OK:
+    return "ok";
+  case PDENET_E_BADARG:
+    return "bad argument (null pointer, non-positive size, even kernel size)";
+  case PDENET_E_UNSUPPORTED:
+    return "unsupported (kernel_size, filters, channels, layers) combination";
+  case PDENET_E_WORKSPACE:
+    return "workspace too small";
+  case PDENET_E_CUDA:
+    return "CUDA error";
+  default:
+    return "unknown error";
+  }
+}
+
+int pdenet_supported(int elem_size, int k, int N, int C, int L) {
+  if (elem_size != 4 && elem_size != 8) return 0;
+  if (k != 3 && k != 5 && k != 7) return 0;
+  if (L < 0 || L > PDENET_MAX_LAYERS) return 0;
+  if (!nc_supported(N, C)) return 0;
+  return pick_vl(N * C, L) != 0;
+}
+
+int pdenet_symnet_param_count(int m, int L) { return symnet_param_count(m, L); }
+
+int pdenet_m2k_f64(const double *m, const double *s, double *kout, int N, int k, void *st) {
+  return sandwich<double>(SW_M2K, m, s, nullptr, kout, N, k, st);
+}
+int pdenet_m2k_f32(const float *m, const double *s, float *kout, int N, int k, void *st) {
+  return sandwich<float>(SW_M2K, m, s, nullptr, kout, N, k, st);
+}
+int pdenet_k2m_f64(const double *kin, const double *s, double *m, int N, int k, void *st) {
+  return sandwich<double>(SW_K2M, kin, s, nullptr, m, N, k, st);
+}
+int pdenet_k2m_f32(const float *kin, const double *s, float *m, int N, int k, void *st) {
+  return sandwich<float>(SW_K2M, kin, s, nullptr, m, N, k, st);
+}
+int pdenet_m2k_bwd_f64(const double *gk, const double *s, const unsigned char *mask, double *gm, int N, int k,
+                       void *st) {
+  return sandwich<double>(SW_M2K_BWD, gk, s, mask, gm, N, k, st);
+}
+int pdenet_m2k_bwd_f32(const float *gk, const double *s, const unsigned char *mask, float *gm, int N, int k,
+                       void *st) {
+  return sandwich<float>(SW_M2K_BWD, gk, s, mask, gm, N, k, st);
+}
+
+int pdenet_fd2d_fwd_f64(const double *u, const double *kernels, double *feats, int B, int C, int H, int W, int k,
+                        int N, void *st) {
+  return fd2d_fwd<double>(u, kernels, feats, B, C, H, W, k, N, st);
+}
+int pdenet_fd2d_fwd_f32(const float *u, const float *kernels, float *feats, int B, int C, int H, int W, int k, int N,
+                        void *st) {
+  return fd2d_fwd<float>(u, kernels, feats, B, C, H, W, k, N, st);
+}
+
+size_t pdenet_fd2d_bwd_workspace_bytes(int k, int N) {
+  const int sms = sm_count();
+  if (sms <= 0 || k <= 0 || N <= 0) return 0;
+  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
+  return (size_t)sms * 8 * N * vlb * sizeof(double);
+}
+int pdenet_fd2d_bwd_f64(const double *u, const double *grad_feats, const double *kernels, double *grad_u,
+                        double *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                        int k, int N, void *st) {
+  return fd2d_bwd<double>(u, grad_feats, kernels, grad_u, grad_kernels, workspace, workspace_bytes, B, C, H, W, k, N,
+                          st);
+}
+int pdenet_fd2d_bwd_f32(const float *u, const float *grad_feats, const float *kernels, float *grad_u,
+                        float *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                        int k, int N, void *st) {
+  return fd2d_bwd<float>(u, grad_feats, kernels, grad_u, grad_kernels, workspace, workspace_bytes, B, C, H, W, k, N,
+                         st);
+}
+
+int pdenet_rollout_fwd_f64(const double *u0, const double *kernels, const double *symnet, double *states, int B,
+                           int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_fwd<double>(u0, kernels, symnet, states, B, C, H, W, k, N, L, steps, dt, st);
+}
+int pdenet_rollout_fwd_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B, int C,
+                           int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_fwd<float>(u0, kernels, symnet, states, B, C, H, W, k, N, L, steps, dt, st);
+}
+
+size_t pdenet_rollout_bwd_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
+                                          int batch_chunk) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, C, H, W, k, N) || L < 0) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  return bwd_layout((size_t)elem_size, B, C, H, W, k, N, L, batch_chunk, sms).total;
+}
+int pdenet_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                           const double *kernels, const double *symnet, double *grad_u0, double *grad_kernels,
+                           double *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                           int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_bwd<double>(u0, states, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt,
+                             st);
+}
+int pdenet_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                           const float *kernels, const float *symnet, float *grad_u0, float *grad_kernels,
+                           float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B, int C,
+                           int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_bwd<float>(u0, states, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels, grad_symnet,
+                            workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st);
+}
+
+int pdenet_linear_rollout_fwd_f64(const double *u0, const double *id_kernel, const double *kernels,
+                                  const double *coe, double *states, int B, int H, int W, int k, int N, int steps,
+                                  double dt, void *st) {
+  return linear_fwd<double>(u0, id_kernel, kernels, coe, states, B, H, W, k, N, steps, dt, st);
+}
+int pdenet_linear_rollout_fwd_f32(const float *u0, const float *id_kernel, const float *kernels, const float *coe,
+                                  float *states, int B, int H, int W, int k, int N, int steps, double dt, void *st) {
+  return linear_fwd<float>(u0, id_kernel, kernels, coe, states, B, H, W, k, N, steps, dt, st);
+}
+size_t pdenet_linear_rollout_bwd_workspace_bytes(int elem_size, int B, int H, int W, int k, int N) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, 1, H, W, k, N)) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  return lin_layout((size_t)elem_size, B, H, W, k, N, sms).total;
+}
+int pdenet_linear_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                                  const double *id_kernel, const double *kernels, const double *coe,
+                                  double *grad_u0, double *grad_id_kernel, double *grad_kernels, double *grad_coe,
+                                  void *workspace, size_t workspace_bytes, int B, int H, int W, int k, int N,
+                                  int steps, double dt, void *st) {
+  return linear_bwd<double>(u0, states, grad_states, grad_mode, id_kernel, kernels, coe, grad_u0, grad_id_kernel,
+                            grad_kernels, grad_coe, workspace, workspace_bytes, B, H, W, k, N, steps, dt, st);
+}
+int pdenet_linear_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                                  const float *id_kernel, const float *kernels, const float *coe, float *grad_u0,
+                                  float *grad_id_kernel, float *grad_kernels, float *grad_coe, void *workspace,
+                                  size_t workspace_bytes, int B, int H, int W, int k, int N, int steps, double dt,
+                                  void *st) {
+  return linear_bwd<float>(u0, states, grad_states, grad_mode, id_kernel, kernels, coe, grad_u0, grad_id_kernel,
+                           grad_kernels, grad_coe, workspace, workspace_bytes, B, H, W, k, N, steps, dt, st);
+}
+
+int pdenet_slab_step_fwd_f64(const double *u_ext, const double *kernels, const double *symnet, double *out, int B,
+                             int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
+                             int N, int L, double dt, void *st) {
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset,
+                               k, N, L, dt, st);
+}
+int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const float *symnet, float *out, int B, int C,
+                             int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N,
+                             int L, double dt, void *st) {
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset, k,
+                              N, L, dt, st);
+}
+
+int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream) {
+  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out) return PDENET_E_BADARG;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  void *scratch = nullptr;
+  if (cudaMalloc(&scratch, 64) != cudaSuccess) return PDENET_E_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sms * 8, block = 256;
+  for (int rep = 0; rep < 2; ++rep) { // first pass warms up
+    cudaEventRecord(e0, st);
+    if (elem_size == 8)
+      fma_peak_kernel<double><<<grid, block, 0, st>>>((double *)scratch, iters, 0.999, 1e-3);
+    else
+      fma_peak_kernel<float><<<grid, block, 0, st>>>((float *)scratch, iters, 0.999f, 1e-3f);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+  }
+  cudaEventElapsedTime(ms_out, e0, e1);
+  *flops_out = 2.0 * 16 * 8 * (double)iters * (double)grid * block;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+} // extern "C"

@@ -1,0 +1,75 @@
+// One translation unit per (PDENET_T, PDENET_K): explicit instantiation of the launchers.
+#include "launch.cuh"
+
+#ifndef PDENET_T
+#error "compile with -DPDENET_T=double|float -DPDENET_K=3|5|7"
+#endif
+
+namespace pdenet {
+
+// opt in to the large dynamic shared-memory carve-out (idempotent, cheap)
+template <typename KernelT> static int allow_smem(KernelT kern, size_t smem) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 0 : -4;
+}
+
+template <typename T, int K, int N, int C, int MODE, int VL>
+static int launch_step_one(const StepParams<T> &p, int grid, cudaStream_t st) {
+  using Cfg = StepCfg<T, K, N, C>;
+  const size_t smem = Cfg::smem_bytes(p.Psym, MODE == MODE_BWD_A);
+  auto kern = step_kernel<T, K, N, C, MODE, VL>;
+  if (allow_smem(kern, smem) != 0) return -4;
+  kern<<<grid, Cfg::NT, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+template <typename T, int K>
+int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int grid, cudaStream_t st) {
+#define PDENET_CASE(NN, CC)                                                                                       \
+  if (N == NN && C == CC) {                                                                                      \
+    if (mode == MODE_FWD) return launch_step_one<T, K, NN, CC, MODE_FWD, 16>(p, grid, st);                       \
+    if (mode == MODE_FEATS) return launch_step_one<T, K, NN, CC, MODE_FEATS, 16>(p, grid, st);                   \
+    if (mode == MODE_BWD_A) {                                                                                    \
+      if constexpr (NN * CC + 1 < 16)                                                                            \
+        if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, grid, st);                         \
+      if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, grid, st);                           \
+    }                                                                                                            \
+  }
+  PDENET_FOR_NC(PDENET_CASE)
+#undef PDENET_CASE
+#define PDENET_CASE(NN)                                                                                           \
+  if (N == NN && C == 1) {                                                                                       \
+    if (mode == MODE_LIN_FWD) return launch_step_one<T, K, NN, 1, MODE_LIN_FWD, 16>(p, grid, st);                \
+    if (mode == MODE_LIN_BWD_A) return launch_step_one<T, K, NN, 1, MODE_LIN_BWD_A, 16>(p, grid, st);            \
+  }
+  PDENET_FOR_LIN(PDENET_CASE)
+#undef PDENET_CASE
+  return -2;
+}
+
+template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st) {
+  using Cfg = AdjCfg<T, K>;
+  const size_t smem = Cfg::smem_bytes(p.N);
+  if (smem > 227 * 1024) return -2;
+  auto kern = adjoint_kernel<T, K>;
+  if (allow_smem(kern, smem) != 0) return -4;
+  kern<<<grid, Cfg::NT, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
+template <typename T, int K> void step_tile(int &tw, int &th) {
+  tw = StepCfg<T, K, 3, 1>::TW;
+  th = StepCfg<T, K, 3, 1>::TH;
+}
+template <typename T, int K> void adjoint_tile(int &tw, int &th) {
+  tw = AdjCfg<T, K>::TW;
+  th = AdjCfg<T, K>::TH;
+}
+
+template int launch_step<PDENET_T, PDENET_K>(int, int, int, int, const StepParams<PDENET_T> &, int, cudaStream_t);
+template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int, cudaStream_t);
+template int adjoint_vlb<PDENET_T, PDENET_K>();
+template void step_tile<PDENET_T, PDENET_K>(int &, int &);
+template void adjoint_tile<PDENET_T, PDENET_K>(int &, int &);
+
+} // namespace pdenet

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's Python model API for the time-stepping path.
+
+The mounted reference has no source (README.md:8 points at absent branches), so the names below
+follow SURVEY.md section 8(b): upstream ``aTEAM.nn.modules.MK.{M2K,K2M}``, ``aTEAM.nn.modules.FD.FD2d``,
+``expr.poly`` and ``polypde.POLYPDE2D`` / ``VariantCoeLinear2d`` (recollection, not verifiable here).
+Same constructor arguments, parameter names and method names; the inner loop of ``multistep`` is
+one call into the fused CUDA rollout (``ops.rollout``) instead of a Python loop over eager ops.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def order_list(max_order: int) -> List[Tuple[int, int]]:
+    """Filter-bank order: total order ascending, then order along H ascending."""
+    return [(j, o - j) for o in range(max_order + 1) for j in range(o + 1)]
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class M2K(nn.Module):
+    """Moment matrix -> convolution kernel (row a2).  ``shape`` is the kernel shape (k, k)."""
+
+    def __init__(self, shape):
+        super().__init__()
+        self.shape = _pair(shape)
+
+    def forward(self, m: torch.Tensor) -> torch.Tensor:
+        return ops.m2k(m)
+
+
+class K2M(nn.Module):
+    """Convolution kernel -> moment matrix (row a3)."""
+
+    def __init__(self, shape):
+        super().__init__()
+        self.shape = _pair(shape)
+
+    def forward(self, k: torch.Tensor) -> torch.Tensor:
+        return ops.k2m(k)
+
+
+class FD2d(nn.Module):
+    """One learnable periodic finite-difference filter parameterised by its moment matrix
+    (rows a4-a6).  ``order=(o0, o1)``: derivative order along H and W."""
+
+    def __init__(self, kernel_size, order, dx=1.0, constraint="moment", boundary="periodic"):
+        super().__init__()
+        if str(boundary).lower() != "periodic":
+            raise NotImplementedError("only periodic boundaries are on the B200 hot path")
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        if k % 2 == 0 or k > 7:
+            raise ValueError("kernel_size must be odd and <= 7")
+        self.kernel_size = k
+        self.order = tuple(order)
+        self.dx = _pair(dx)
+        self.constraint = constraint
+        m = torch.zeros(k, k, dtype=torch.float64)
+        m[self.order[0], self.order[1]] = 1
+        self.moment = nn.Parameter(m)
+        self.register_buffer("_pinned", self._mask(), persistent=False)
+        self.register_buffer("_init", m.clone(), persistent=False)
+
+    def _mask(self) -> torch.Tensor:
+        k = self.kernel_size
+        mask = torch.zeros(k, k, dtype=torch.bool)
+        c = self.constraint
+        if c == "free" or c == 0:
+            return mask
+        if c == "frozen":
+            return ~mask
+        acc = 1 if c == "moment" else int(c)
+        s = self.order[0] + self.order[1] + acc
+        i = torch.arange(k)
+        return (i[:, None] + i[None, :]) < s
+
+    @property
+    def scale(self) -> float:
+        return 1.0 / (self.dx[0] ** self.order[0] * self.dx[1] ** self.order[1])
+
+    @property
+    def kernel(self) -> torch.Tensor:
+        return ops.m2k(self.moment[None], [self.scale], self._pinned[None])[0]
+
+    def x_proj(self, *args, **kw):
+        """Re-impose the pinned moment entries (sum-rule constraint) after an optimiser update."""
+        with torch.no_grad():
+            self.moment.data = torch.where(self._pinned, self._init.to(self.moment.dtype), self.moment.data)
+
+    def grad_proj(self, *args, **kw):
+        """Zero the gradient of pinned moment entries."""
+        if self.moment.grad is not None:
+            self.moment.grad.data.masked_fill_(self._pinned, 0)
+
+    def forward(self, u: torch.Tensor) -> torch.Tensor:
+        """u [B,C,H,W] -> this derivative of every channel, [B,C,H,W]."""
+        shape = u.shape
+        u4 = u.reshape(-1, 1, shape[-2], shape[-1])
+        return ops.fd2d(u4, self.kernel[None]).reshape(shape)
+
+
+class poly(nn.Module):
+    """SymNet (row a7): ``hidden_layers`` product units, then a linear read-out."""
+
+    def __init__(self, hidden_layers, channel_num, channel_names=None):
+        super().__init__()
+        self.hidden_layers = hidden_layers
+        self.channel_num = channel_num
+        self.channel_names = list(channel_names) if channel_names is not None else [
+            "u%d" % i for i in range(channel_num)]
+        for i in range(hidden_layers):
+            lin = nn.Linear(channel_num + i, 2).to(torch.float64)
+            lin.weight.data.zero_()
+            lin.bias.data.zero_()
+            self.add_module("layer%d" % i, lin)
+        fin = nn.Linear(channel_num + hidden_layers, 1).to(torch.float64)
+        fin.weight.data.zero_()
+        fin.bias.data.zero_()
+        self.add_module("layer_final", fin)
+
+    def flat_params(self) -> torch.Tensor:
+        """The flat parameter vector in the C-ABI layout (W_i, b_i ..., w_f, b_f)."""
+        parts = []
+        for i in range(self.hidden_layers):
+            lin = getattr(self, "layer%d" % i)
+            parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+        parts += [self.layer_final.weight.reshape(-1), self.layer_final.bias.reshape(-1)]
+        return torch.cat(parts)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        """inputs [..., channel_num] -> [...]; standalone evaluation (the rollout uses the fused kernel)."""
+        return ops.symnet_eval(inputs, self.flat_params(), self.hidden_layers)
+
+
+class POLYPDE2D(nn.Module):
+    """PDE-Net 2.0 model (rows a8-a10): ``forward(init, T)`` = state after ``round(T/dt)`` Euler steps."""
+
+    def __init__(self, dt, dx, kernel_size, max_order, constraint, channel_names, hidden_layers=2,
+                 scheme="central", dtype=torch.float64, batch_chunk=0):
+        super().__init__()
+        if scheme != "central":
+            raise NotImplementedError("scheme=%r: only the central scheme is on the B200 hot path" % scheme)
+        self.dt, self.dx = float(dt), _pair(dx)
+        self.kernel_size, self.max_order, self.constraint = kernel_size, max_order, constraint
+        self.channel_names = list(channel_names.split(",")) if isinstance(channel_names, str) else list(channel_names)
+        self.channel_num = len(self.channel_names)
+        self.hidden_layers = hidden_layers
+        self.batch_chunk = batch_chunk
+        self.orders = order_list(max_order)
+        self._fd_names = []
+        for (o0, o1) in self.orders:
+            name = "fd%d%d" % (o0, o1)
+            self.add_module(name, FD2d(kernel_size, (o0, o1), dx=dx, constraint=constraint))
+            self._fd_names.append(name)
+        allch = [c + "_%d%d" % o for c in self.channel_names for o in self.orders]
+        for c in range(self.channel_num):
+            self.add_module("poly%d" % c, poly(hidden_layers, len(allch), allch))
+        self.to(dtype)
+
+    # ---- parameter groups / projection hooks (upstream names)
+    @property
+    def fds(self):
+        return [getattr(self, n) for n in self._fd_names]
+
+    @property
+    def polys(self):
+        return [getattr(self, "poly%d" % c) for c in range(self.channel_num)]
+
+    def diff_params(self):
+        return (fd.moment for fd in self.fds)
+
+    def expr_params(self):
+        return (p for pl in self.polys for p in pl.parameters())
+
+    def diff_x_proj(self, *a, **kw):
+        for fd in self.fds:
+            fd.x_proj()
+
+    def diff_grad_proj(self, *a, **kw):
+        for fd in self.fds:
+            fd.grad_proj()
+
+    # ---- pieces of the step
+    def scaled_kernels(self) -> torch.Tensor:
+        fds = self.fds
+        moments = torch.stack([fd.moment for fd in fds])
+        mask = torch.stack([fd._pinned for fd in fds])
+        return ops.m2k(moments, [fd.scale for fd in fds], mask)
+
+    def symnet_flat(self) -> torch.Tensor:
+        return torch.stack([pl.flat_params() for pl in self.polys])
+
+    def UInputs(self, u: torch.Tensor) -> torch.Tensor:
+        """[B,C,H,W] -> channels-last derivative features [B,H,W,C*N]."""
+        return ops.fd2d(u, self.scaled_kernels()).permute(0, 2, 3, 1)
+
+    def RightHandItems(self, u: torch.Tensor) -> torch.Tensor:
+        """F(u) [B,C,H,W] = (one fused step - u) / dt."""
+        return (self.predict(u) - u) / self.dt
+
+    def predict(self, u: torch.Tensor) -> torch.Tensor:
+        return self.multistep(u, self.dt)
+
+    def multistep(self, inputs: torch.Tensor, T: float, all_states: bool = False) -> torch.Tensor:
+        steps = max(1, int(round(T / self.dt)))
+        return ops.rollout(inputs, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.dt, steps,
+                           last_only=not all_states, batch_chunk=self.batch_chunk)
+
+    def forward(self, init: torch.Tensor, T: float) -> torch.Tensor:
+        return self.multistep(init, T)
+
+
+class VariantCoeLinear2d(nn.Module):
+    """PDE-Net 1 linear variable-coefficient model (row a12):
+    ``u+ = D0*u + dt * sum_n c_n(x,y) (D_n*u)`` with learnable D0 and coefficient fields c_n."""
+
+    def __init__(self, kernel_size, max_order, dx, dt, mesh_size, constraint="moment", dtype=torch.float64):
+        super().__init__()
+        self.dt, self.dx = float(dt), _pair(dx)
+        self.kernel_size, self.max_order = kernel_size, max_order
+        self.mesh_size = _pair(mesh_size)
+        self.orders = [o for o in order_list(max_order) if o != (0, 0)]
+        self.id = FD2d(kernel_size, (0, 0), dx=dx, constraint=constraint)
+        self._fd_names = []
+        for (o0, o1) in self.orders:
+            name = "fd%d%d" % (o0, o1)
+            self.add_module(name, FD2d(kernel_size, (o0, o1), dx=dx, constraint=constraint))
+            self._fd_names.append(name)
+        # coefficient fields on the grid (upstream interpolates them from a coarse mesh once per
+        # call -- SURVEY "next" row f-2; here they are direct parameters)
+        self.coe = nn.Parameter(torch.zeros(len(self.orders), *self.mesh_size, dtype=torch.float64))
+        self.to(dtype)
+
+    @property
+    def fds(self):
+        return [getattr(self, n) for n in self._fd_names]
+
+    def diff_params(self):
+        return (fd.moment for fd in [self.id] + self.fds)
+
+    def coe_params(self):
+        return iter([self.coe])
+
+    def diff_x_proj(self, *a, **kw):
+        for fd in [self.id] + self.fds:
+            fd.x_proj()
+
+    def diff_grad_proj(self, *a, **kw):
+        for fd in [self.id] + self.fds:
+            fd.grad_proj()
+
+    def scaled_kernels(self):
+        fds = [self.id] + self.fds
+        moments = torch.stack([fd.moment for fd in fds])
+        mask = torch.stack([fd._pinned for fd in fds])
+        return ops.m2k(moments, [fd.scale for fd in fds], mask)
+
+    def forward(self, init: torch.Tensor, stepnum: int, all_states: bool = False) -> torch.Tensor:
+        ks = self.scaled_kernels()
+        return ops.linear_rollout(init, ks[0], ks[1:], self.coe, self.dt, int(stepnum), last_only=not all_states)

@@ -1,0 +1,287 @@
+"""torch.autograd bridge over the C-ABI: the only place Python touches the CUDA hot path.
+
+Each function takes CUDA tensors, hands raw device pointers + the current stream to
+libpdenet_b200.so, and wires the reverse kernels into autograd.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("pdenet_b200: `%s` must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("pdenet_b200: `%s` has dtype %s, expected %s" % (name, t.dtype, dtype))
+    return t.contiguous()
+
+
+def _scale_array(scale: Optional[Sequence[float]], N: int):
+    if scale is None:
+        return None
+    if len(scale) != N:
+        raise ValueError("scale must have one entry per filter")
+    return (C.c_double * N)(*[float(s) for s in scale])
+
+
+def symnet_param_count(m: int, L: int) -> int:
+    return sum(2 * (m + i) + 2 for i in range(L)) + (m + L) + 1
+
+
+# ------------------------------------------------------------------------------ rows a1-a3
+class _M2K(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, moments, scale, mask):
+        moments = _req(moments, "moments")
+        N, k, _ = moments.shape
+        out = torch.empty_like(moments)
+        _lib.check(_lib.fn("pdenet_m2k", moments.dtype)(_ptr(moments), _scale_array(scale, N), _ptr(out), N, k,
+                                                        _stream()), "pdenet_m2k")
+        ctx.scale, ctx.mask = scale, mask
+        return out
+
+    @staticmethod
+    def backward(ctx, gk):
+        gk = _req(gk, "grad_kernels")
+        N, k, _ = gk.shape
+        gm = torch.empty_like(gk)
+        _lib.check(_lib.fn("pdenet_m2k_bwd", gk.dtype)(_ptr(gk), _scale_array(ctx.scale, N), _ptr(ctx.mask),
+                                                       _ptr(gm), N, k, _stream()), "pdenet_m2k_bwd")
+        return gm, None, None
+
+
+def m2k(moments: torch.Tensor, scale: Optional[Sequence[float]] = None,
+        pinned_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kernels[n] = scale[n] * A^-1 moments[n] A^-T.  ``pinned_mask``
+    (uint8 [N,k,k] on the device) zeroes the gradient of pinned moment entries (row a4)."""
+    lead = moments.shape[:-2]
+    k = moments.shape[-1]
+    flat = moments.reshape(-1, k, k)
+    if pinned_mask is not None:
+        pinned_mask = _req(pinned_mask.reshape(-1, k, k).to(torch.uint8), "pinned_mask")
+    return _M2K.apply(flat, scale, pinned_mask).reshape(*lead, k, k)
+
+
+def k2m(kernels: torch.Tensor, scale: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """moments[n] = A (kernels[n] / scale[n]) A^T (row a3; inspection only, no autograd)."""
+    lead = kernels.shape[:-2]
+    k = kernels.shape[-1]
+    flat = _req(kernels.detach().reshape(-1, k, k), "kernels")
+    out = torch.empty_like(flat)
+    _lib.check(_lib.fn("pdenet_k2m", flat.dtype)(_ptr(flat), _scale_array(scale, flat.shape[0]), _ptr(out),
+                                                 flat.shape[0], k, _stream()), "pdenet_k2m")
+    return out.reshape(*lead, k, k)
+
+
+# ------------------------------------------------------------------------------ rows a5-a6
+def fd2d_features(u: torch.Tensor, kernels: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] x [N,k,k] -> [B,C*N,H,W] periodic cross-correlation (no autograd; the
+    differentiable path is :func:`rollout`)."""
+    u = _req(u.detach(), "u")
+    kernels = _req(kernels.detach(), "kernels", u.dtype)
+    B, Cc, H, W = u.shape
+    N, k, _ = kernels.shape
+    out = torch.empty(B, Cc * N, H, W, dtype=u.dtype, device=u.device)
+    _lib.check(_lib.fn("pdenet_fd2d_fwd", u.dtype)(_ptr(u), _ptr(kernels), _ptr(out), B, Cc, H, W, k, N,
+                                                   _stream()), "pdenet_fd2d_fwd")
+    return out
+
+
+class _FD2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, kernels):
+        ctx.save_for_backward(u, kernels)
+        return fd2d_features(u, kernels)
+
+    @staticmethod
+    def backward(ctx, gf):
+        u, kernels = ctx.saved_tensors
+        u, kernels = _req(u, "u"), _req(kernels, "kernels", u.dtype)
+        gf = _req(gf, "grad_feats", u.dtype)
+        B, Cc, H, W = u.shape
+        N, k, _ = kernels.shape
+        nbytes = _lib.lib().pdenet_fd2d_bwd_workspace_bytes(k, N)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u.device)
+        gu = torch.empty_like(u) if ctx.needs_input_grad[0] else None
+        gk = torch.empty_like(kernels) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.fn("pdenet_fd2d_bwd", u.dtype)(_ptr(u), _ptr(gf), _ptr(kernels), _ptr(gu), _ptr(gk),
+                                                       _ptr(ws), nbytes, B, Cc, H, W, k, N, _stream()),
+                   "pdenet_fd2d_bwd")
+        return gu, gk
+
+
+def fd2d(u: torch.Tensor, kernels: torch.Tensor) -> torch.Tensor:
+    """Differentiable periodic FD2d bank: [B,C,H,W] x [N,k,k] -> [B,C*N,H,W] (rows a5-a6, a11)."""
+    return _FD2d.apply(u, kernels)
+
+
+def symnet_eval(feat: torch.Tensor, flat: torch.Tensor, L: int) -> torch.Tensor:
+    """Standalone SymNet evaluation ``feat [..., m] -> [...]`` with the flat C-ABI parameter
+    layout.  Cold path (inspection / unit use of ``expr.poly``): plain tensor ops on the
+    caller's device; the time-stepping path evaluates SymNet inside the fused rollout kernel."""
+    m = feat.shape[-1]
+    o, h = 0, feat
+    for i in range(L):
+        mi = m + i
+        Wt = flat[o:o + 2 * mi].reshape(2, mi)
+        b = flat[o + 2 * mi:o + 2 * mi + 2]
+        o += 2 * mi + 2
+        pq = h @ Wt.t() + b
+        h = torch.cat([h, pq[..., :1] * pq[..., 1:]], dim=-1)
+    return h @ flat[o:o + m + L] + flat[o + m + L]
+
+
+# ------------------------------------------------------------------------------ rows a7-a11
+class _Rollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk):
+        u0 = _req(u0, "u0")
+        kernels = _req(kernels, "kernels", u0.dtype)
+        symnet = _req(symnet, "symnet", u0.dtype)
+        B, Cc, H, W = u0.shape
+        N, k, _ = kernels.shape
+        if tuple(symnet.shape) != (Cc, symnet_param_count(Cc * N, L)):
+            raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
+                             % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
+        states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
+        _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
+            _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
+            _stream()), "pdenet_rollout_fwd")
+        ctx.cfg = (L, float(dt), steps, last_only, batch_chunk)
+        if last_only:  # `states` is an intermediate: keep it on ctx (no cycle, it is not an output)
+            ctx.save_for_backward(u0, kernels, symnet)
+            ctx.states = states
+            return states[-1]
+        ctx.save_for_backward(u0, kernels, symnet, states)
+        return states
+
+    @staticmethod
+    def backward(ctx, grad):
+        if ctx.cfg[3]:
+            (u0, kernels, symnet), states = ctx.saved_tensors, ctx.states
+        else:
+            u0, kernels, symnet, states = ctx.saved_tensors
+        L, dt, steps, last_only, batch_chunk = ctx.cfg
+        B, Cc, H, W = u0.shape
+        N, k, _ = kernels.shape
+        grad = _req(grad, "grad_states", u0.dtype)
+        es = u0.element_size()
+        nbytes = _lib.lib().pdenet_rollout_bwd_workspace_bytes(es, B, Cc, H, W, k, N, L, batch_chunk)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
+        need_u, need_k, need_s = ctx.needs_input_grad[:3]
+        gu = torch.empty_like(u0) if need_u else None
+        gk = torch.empty_like(kernels) if need_k else None
+        gs = torch.empty_like(symnet) if need_s else None
+        _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_LAST if last_only else _lib.GRAD_ALL, _ptr(kernels),
+            _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps,
+            dt, _stream()), "pdenet_rollout_bwd")
+        return gu, gk, gs, None, None, None, None, None
+
+
+def rollout(u0: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
+            last_only: bool = False, batch_chunk: int = 0) -> torch.Tensor:
+    """Fused forward-Euler rollout ``u <- u + dt*SymNet(FD2d(u))`` (rows a5-a10), differentiable
+    w.r.t. ``u0``, the scaled ``kernels`` [N,k,k] and the flat ``symnet`` [C,Psym] (row a11).
+
+    Returns the states after every step ``[steps,B,C,H,W]`` (or only the last one)."""
+    if steps < 1:
+        raise ValueError("steps must be >= 1")
+    return _Rollout.apply(u0, kernels, symnet, int(L), float(dt), int(steps), bool(last_only), int(batch_chunk))
+
+
+# ------------------------------------------------------------------------------ row a12
+class _LinearRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u0, id_kernel, kernels, coe, dt, steps, last_only):
+        u0 = _req(u0, "u0")
+        id_kernel = _req(id_kernel, "id_kernel", u0.dtype)
+        kernels = _req(kernels, "kernels", u0.dtype)
+        coe = _req(coe, "coe", u0.dtype)
+        B, H, W = u0.shape
+        N, k, _ = kernels.shape
+        if tuple(coe.shape) != (N, H, W):
+            raise ValueError("coe must be [N,H,W]")
+        states = torch.empty(steps, B, H, W, dtype=u0.dtype, device=u0.device)
+        _lib.check(_lib.fn("pdenet_linear_rollout_fwd", u0.dtype)(
+            _ptr(u0), _ptr(id_kernel), _ptr(kernels), _ptr(coe), _ptr(states), B, H, W, k, N, steps, float(dt),
+            _stream()), "pdenet_linear_rollout_fwd")
+        ctx.cfg = (float(dt), steps, last_only)
+        if last_only:
+            ctx.save_for_backward(u0, id_kernel, kernels, coe)
+            ctx.states = states
+            return states[-1]
+        ctx.save_for_backward(u0, id_kernel, kernels, coe, states)
+        return states
+
+    @staticmethod
+    def backward(ctx, grad):
+        if ctx.cfg[2]:
+            (u0, id_kernel, kernels, coe), states = ctx.saved_tensors, ctx.states
+        else:
+            u0, id_kernel, kernels, coe, states = ctx.saved_tensors
+        dt, steps, last_only = ctx.cfg
+        B, H, W = u0.shape
+        N, k, _ = kernels.shape
+        grad = _req(grad, "grad_states", u0.dtype)
+        nbytes = _lib.lib().pdenet_linear_rollout_bwd_workspace_bytes(u0.element_size(), B, H, W, k, N)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
+        need = ctx.needs_input_grad
+        gu = torch.empty_like(u0) if need[0] else None
+        g0 = torch.empty_like(id_kernel) if need[1] else None
+        gk = torch.empty_like(kernels) if need[2] else None
+        gc = torch.empty_like(coe) if need[3] else None
+        _lib.check(_lib.fn("pdenet_linear_rollout_bwd", u0.dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_LAST if last_only else _lib.GRAD_ALL, _ptr(id_kernel),
+            _ptr(kernels), _ptr(coe), _ptr(gu), _ptr(g0), _ptr(gk), _ptr(gc), _ptr(ws), nbytes, B, H, W, k, N,
+            steps, dt, _stream()), "pdenet_linear_rollout_bwd")
+        return gu, g0, gk, gc, None, None, None
+
+
+def linear_rollout(u0, id_kernel, kernels, coe, dt: float, steps: int, last_only: bool = False):
+    """PDE-Net 1 rollout ``u <- K0*u + dt*sum_n coe_n (K_n*u)`` (row a12); u0 [B,H,W]."""
+    if steps < 1:
+        raise ValueError("steps must be >= 1")
+    return _LinearRollout.apply(u0, id_kernel, kernels, coe, float(dt), int(steps), bool(last_only))
+
+
+def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, halo: int,
+              out: Optional[torch.Tensor] = None, out_row_offset: int = 0) -> torch.Tensor:
+    """One forward step on a slab [B,C,Hs+2*halo,W] whose ghost rows are already filled
+    (slab domain decomposition).  Writes rows [out_row_offset, out_row_offset+Hs)
+    of ``out`` (default: a fresh [B,C,Hs,W])."""
+    u_ext = _req(u_ext.detach(), "u_ext")
+    kernels = _req(kernels.detach(), "kernels", u_ext.dtype)
+    symnet = _req(symnet.detach(), "symnet", u_ext.dtype)
+    B, Cc, He, W = u_ext.shape
+    Hs = He - 2 * halo
+    N, k, _ = kernels.shape
+    if out is None:
+        out = torch.empty(B, Cc, Hs, W, dtype=u_ext.dtype, device=u_ext.device)
+    if not out.is_contiguous():
+        raise ValueError("out must be contiguous")
+    _lib.check(_lib.fn("pdenet_slab_step_fwd", u_ext.dtype)(
+        _ptr(u_ext), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, Hs, W, halo, out.shape[2], out_row_offset, k,
+        N, L, float(dt), _stream()), "pdenet_slab_step_fwd")
+    return out
+
+
+def fma_peak(dtype=torch.float64, iters: int = 4096):
+    """Measured CUDA-core FMA throughput in FLOP/s (register-only loop)."""
+    flops, ms = C.c_double(0), C.c_float(0)
+    _lib.check(_lib.lib().pdenet_fma_peak(8 if dtype == torch.float64 else 4, iters, C.byref(flops), C.byref(ms),
+                                          _stream()), "pdenet_fma_peak")
+    return flops.value / (ms.value * 1e-3)

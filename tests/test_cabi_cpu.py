@@ -1,0 +1,85 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares; host-side module logic (constraint masks, parameter layout, projection hooks)."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as G
+    G.build()
+    import pdenet_b200
+    return pdenet_b200
+
+
+def test_header_symbols_exported(built):
+    from pdenet_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pdenet_b200.h")).read()
+    declared = set(re.findall(r"PDENET_API\s+[\w\s\*]*?\b(pdenet_\w+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.exported_symbols())
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (pdenet_\w+)", nm))
+    assert declared <= exported, declared - exported
+    lib = _lib.lib()  # loads with ctypes; no compute call without a GPU
+    assert lib.pdenet_version() >= 100
+    assert lib.pdenet_symnet_param_count(12, 2) == 69
+    assert lib.pdenet_error_string(-2).decode().startswith("unsupported")
+
+
+def test_sass_is_sm100a_cuda_core_code(built):
+    from pdenet_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(built):
+    with pytest.raises(RuntimeError):
+        built.fd2d_features(torch.zeros(1, 2, 8, 8, dtype=torch.float64), torch.zeros(6, 5, 5, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        built.rollout(torch.zeros(1, 2, 8, 8, dtype=torch.float64), torch.zeros(6, 5, 5, dtype=torch.float64),
+                      torch.zeros(2, 69, dtype=torch.float64), 2, 1e-2, 1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pde-net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), f
+
+
+def test_module_layout_and_masks(built):
+    from oracle import pdenet_oracle as O
+    m = built.POLYPDE2D(1e-2, 0.1, 7, 2, "moment", "u,v", hidden_layers=2)
+    assert [fd.order for fd in m.fds] == O.order_list(2)
+    for fd in m.fds:
+        assert torch.equal(fd._pinned, O.pinned_mask(7, fd.order, "moment"))
+    assert m.symnet_flat().shape == (2, O.symnet_param_count(12, 2))
+    # flat layout == oracle's symnet_unpack
+    with torch.no_grad():
+        for i, p in enumerate(m.poly0.parameters()):
+            p.copy_(torch.arange(p.numel(), dtype=torch.float64).reshape(p.shape) + 100 * i)
+    hidden, (wf, bf) = O.symnet_unpack(m.poly0.flat_params(), 12, 2)
+    assert torch.equal(hidden[0][0], m.poly0.layer0.weight) and torch.equal(hidden[1][1], m.poly0.layer1.bias)
+    assert torch.equal(wf, m.poly0.layer_final.weight[0]) and torch.equal(bf, m.poly0.layer_final.bias)
+    # standalone SymNet evaluation (cold path) == oracle
+    x = torch.randn(4, 5, 12, dtype=torch.float64)
+    assert torch.allclose(m.poly0(x), O.symnet_apply(x, m.poly0.flat_params(), 2), atol=1e-12)
+    # x_proj restores pinned entries, grad_proj zeroes their gradient
+    fd = m.fd11
+    with torch.no_grad():
+        fd.moment.add_(1.0)
+    fd.x_proj()
+    assert torch.equal(fd.moment.detach()[fd._pinned], fd._init[fd._pinned])
+    fd.moment.grad = torch.ones_like(fd.moment)
+    fd.grad_proj()
+    assert (fd.moment.grad[fd._pinned] == 0).all() and (fd.moment.grad[~fd._pinned] == 1).all()
+    assert len(list(m.diff_params())) == 6 and len(list(m.expr_params())) == 12

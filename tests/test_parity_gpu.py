@@ -1,0 +1,324 @@
+"""Parity of the CUDA hot path (through the C-ABI) against the CPU oracle.
+
+Tolerances are the north star's: fp64 <= 1e-10 relative per step (states and gradients),
+fp32 <= 1e-5.  Marked gpu: run on the B200 box.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def P(cuda_device):
+    import pdenet_b200
+    return pdenet_b200
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+def make_model(k, max_order, C, L, dx, seed, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(max_order)
+    N = len(orders)
+    M = O.initial_moments(k, orders) + 1e-2 * torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    scales = O.filter_scales(orders, dx)
+    sym = 0.1 * torch.randn(C, O.symnet_param_count(C * N, L), generator=g, dtype=torch.float64)
+    return orders, M, scales, sym
+
+
+def smooth_field(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.arange(H, dtype=torch.float64) * (2 * math.pi / H)
+    x = torch.arange(W, dtype=torch.float64) * (2 * math.pi / W)
+    Y, X = torch.meshgrid(y, x, indexing="ij")
+    u = torch.zeros(B, C, H, W, dtype=torch.float64)
+    for p in range(-2, 3):
+        for q in range(-2, 3):
+            a = torch.randn(B, C, 1, 1, generator=g, dtype=torch.float64)
+            b = torch.randn(B, C, 1, 1, generator=g, dtype=torch.float64)
+            u += a * torch.cos(p * X + q * Y) + b * torch.sin(p * X + q * Y)
+    return u / u.abs().amax(dim=(2, 3), keepdim=True)
+
+
+# ------------------------------------------------------------------ rows a1-a4
+@pytest.mark.parametrize("k", [3, 5, 7])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_m2k_k2m(P, cuda_device, k, dtype):
+    g = torch.Generator().manual_seed(k)
+    M = torch.randn(6, k, k, generator=g, dtype=torch.float64)
+    scales = [1.0, 2.0, 0.5, 30.0, 7.0, 0.1]
+    ref = O.m2k(M) * torch.tensor(scales)[:, None, None]
+    Md = M.to(cuda_device, dtype)
+    K = P.m2k(Md, scales)
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    assert rel(K, ref) < tol
+    assert rel(P.k2m(K, scales), M) < (1e-10 if dtype == torch.float64 else 2e-3)
+    # first-derivative KAT through the CUDA path (KAT-1)
+    oh = torch.zeros(1, k, k, dtype=torch.float64)
+    oh[0, 0, 1] = 1
+    row = {3: [-1 / 2, 0, 1 / 2], 5: [1 / 12, -2 / 3, 0, 2 / 3, -1 / 12],
+           7: [-1 / 60, 3 / 20, -3 / 4, 0, 3 / 4, -3 / 20, 1 / 60]}[k]
+    Kd = P.m2k(oh.to(cuda_device, dtype))[0].cpu().double()
+    assert torch.allclose(Kd[(k - 1) // 2], torch.tensor(row, dtype=torch.float64), atol=1e-6 if dtype == torch.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_m2k_backward_and_mask(P, cuda_device, k):
+    g = torch.Generator().manual_seed(10 + k)
+    M = torch.randn(3, k, k, generator=g, dtype=torch.float64)
+    w = torch.randn(3, k, k, generator=g, dtype=torch.float64)
+    scales = [1.0, 4.0, 16.0]
+    Mc = M.clone().requires_grad_(True)
+    ((O.m2k(Mc) * torch.tensor(scales)[:, None, None]) * w).sum().backward()
+    mask = torch.stack([O.pinned_mask(k, o, "moment") for o in [(0, 0), (0, 1), (1, 1)]])
+    Md = M.to(cuda_device).requires_grad_(True)
+    (P.m2k(Md, scales, mask.to(cuda_device)) * w.to(cuda_device)).sum().backward()
+    ref = Mc.grad.masked_fill(mask, 0)
+    assert rel(Md.grad, ref) < 1e-11
+    assert (Md.grad.cpu()[mask] == 0).all()
+
+
+# ------------------------------------------------------------------ rows a5-a6
+@pytest.mark.parametrize("k,max_order,C,H,W", [
+    (7, 2, 2, 100, 100), (5, 2, 1, 37, 53), (3, 1, 3, 8, 9), (7, 1, 1, 5, 6), (5, 4, 1, 50, 50), (7, 3, 1, 33, 70),
+    (7, 2, 3, 40, 24),
+])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fd2d_features(P, cuda_device, k, max_order, C, H, W, dtype):
+    orders, M, scales, _ = make_model(k, max_order, C, 0, 0.37, 3)
+    Ks = O.scaled_kernels(M, scales)
+    u = smooth_field(2, C, H, W, 4)
+    ref = O.fd2d_apply(u, Ks)
+    out = P.fd2d_features(u.to(cuda_device, dtype), Ks.to(cuda_device, dtype))
+    assert rel(out, ref) < (1e-12 if dtype == torch.float64 else 2e-5)
+
+
+def test_fd2d_autograd(P, cuda_device):
+    k, C, H, W = 5, 2, 21, 34
+    orders, M, scales, _ = make_model(k, 2, C, 0, 0.5, 5)
+    Ks = O.scaled_kernels(M, scales)
+    u = smooth_field(2, C, H, W, 6)
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(2, C * len(orders), H, W, generator=g, dtype=torch.float64)
+    uc, Kc = u.clone().requires_grad_(True), Ks.clone().requires_grad_(True)
+    (O.fd2d_apply(uc, Kc) * w).sum().backward()
+    ud, Kd = u.to(cuda_device).requires_grad_(True), Ks.to(cuda_device).requires_grad_(True)
+    (P.fd2d(ud, Kd) * w.to(cuda_device)).sum().backward()
+    assert rel(ud.grad, uc.grad) < 1e-11
+    assert rel(Kd.grad, Kc.grad) < 1e-11
+
+
+# ------------------------------------------------------------------ rows a7-a11
+CASES = [
+    # k, max_order, C, L, B, H, W, steps, dx, dt
+    (7, 2, 2, 2, 8, 100, 100, 1, 2 * math.pi / 100, 1e-2),   # BASELINE config 1
+    (7, 2, 2, 2, 2, 128, 128, 3, 2 * math.pi / 128, 1e-3),   # config 3 shape, short
+    (5, 2, 2, 2, 3, 37, 53, 4, 0.2, 1e-2),                   # ragged tiles
+    (3, 1, 1, 1, 2, 8, 9, 3, 0.5, 1e-2),                     # tiny grid, wraps several times
+    (7, 2, 1, 3, 2, 20, 70, 2, 0.3, 1e-2),
+    (5, 2, 2, 0, 2, 33, 31, 2, 0.3, 1e-2),                   # L = 0: linear SymNet
+    (5, 2, 2, 5, 2, 40, 40, 2, 0.3, 1e-2),                   # deep SymNet (VL=32 path)
+    (7, 1, 3, 2, 2, 16, 64, 2, 0.3, 1e-2),
+    (5, 3, 1, 2, 2, 30, 30, 2, 0.3, 1e-2),
+    (5, 2, 3, 2, 1, 30, 66, 2, 0.3, 1e-2),
+]
+
+
+def run_both(P, dev, case, dtype, grad_all, batch_chunk=0):
+    k, max_order, C, L, B, H, W, steps, dx, dt = case
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 7)
+    Ks = O.scaled_kernels(M, scales)
+    u0 = smooth_field(B, C, H, W, 8)
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(steps, B, C, H, W, generator=g, dtype=torch.float64)
+    if not grad_all:
+        w[:-1] = 0
+    # oracle (fp64 CPU)
+    uc, Kc, sc = u0.clone().requires_grad_(True), Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    st_ref = torch.stack(O.rollout(uc, Kc, sc, L, dt, steps))
+    (st_ref * w).sum().backward()
+    # CUDA
+    ud = u0.to(dev, dtype).requires_grad_(True)
+    Kd = Ks.to(dev, dtype).requires_grad_(True)
+    sd = sym.to(dev, dtype).requires_grad_(True)
+    wd = w.to(dev, dtype)
+    if grad_all:
+        st = P.rollout(ud, Kd, sd, L, dt, steps, batch_chunk=batch_chunk)
+        (st * wd).sum().backward()
+    else:
+        last = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True, batch_chunk=batch_chunk)
+        (last * wd[-1]).sum().backward()
+        st = last[None]
+        st_ref = st_ref[-1:]
+    return (st, ud.grad, Kd.grad, sd.grad), (st_ref, uc.grad, Kc.grad, sc.grad)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("grad_all", [False, True])
+def test_rollout_parity_fp64(P, cuda_device, case, grad_all):
+    got, ref = run_both(P, cuda_device, case, torch.float64, grad_all)
+    steps = case[7]
+    names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
+    for n, a, b in zip(names, got, ref):
+        assert rel(a, b) < TOL[torch.float64] * max(1, steps), (n, rel(a, b))
+
+
+@pytest.mark.parametrize("case", CASES[:5])
+def test_rollout_parity_fp32(P, cuda_device, case):
+    got, ref = run_both(P, cuda_device, case, torch.float32, True)
+    steps = case[7]
+    names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
+    for n, a, b in zip(names, got, ref):
+        # the fp64 oracle is the truth; fp32 round-off scales with the 1/dx^2 filter taps
+        assert rel(a, b) < 20 * TOL[torch.float32] * max(1, steps), (n, rel(a, b))
+
+
+def test_batch_chunk_and_determinism(P, cuda_device):
+    case = (5, 2, 2, 2, 5, 37, 53, 3, 0.2, 1e-2)
+    a, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0)
+    b, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0)
+    c, ref = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=2)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)  # bit-identical repeat
+    for x, y in zip(c, ref):
+        assert rel(x, y) < 1e-10 * 3
+
+
+def test_frozen_filters_and_no_input_grad(P, cuda_device):
+    case = CASES[2]
+    k, max_order, C, L, B, H, W, steps, dx, dt = case
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 7)
+    Ks = O.scaled_kernels(M, scales)
+    u0 = smooth_field(B, C, H, W, 8)
+    sc = sym.clone().requires_grad_(True)
+    O.rollout(u0, Ks, sc, L, dt, steps)[-1].square().sum().backward()
+    sd = sym.to(cuda_device).requires_grad_(True)
+    P.rollout(u0.to(cuda_device), Ks.to(cuda_device), sd, L, dt, steps, last_only=True).square().sum().backward()
+    assert rel(sd.grad, sc.grad) < 1e-10 * steps
+
+
+def test_shift_equivariance_large(P, cuda_device):
+    """Size-independent property at a size the oracle is too slow for (KAT-5 on the CUDA path)."""
+    k, max_order, C, L, dx, dt = 7, 2, 2, 2, 2 * math.pi / 512, 1e-3
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 11)
+    Ks = O.scaled_kernels(M, scales).to(cuda_device)
+    sym = sym.to(cuda_device)
+    u = smooth_field(2, C, 512, 512, 12).to(cuda_device)
+    a = P.rollout(torch.roll(u, (37, -91), (2, 3)), Ks, sym, L, dt, 2, last_only=True)
+    b = torch.roll(P.rollout(u, Ks, sym, L, dt, 2, last_only=True), (37, -91), (2, 3))
+    assert rel(a, b) < 1e-12
+
+
+# ------------------------------------------------------------------ module API (boundary, 8b)
+def test_polypde2d_module_matches_oracle(P, cuda_device):
+    dt, dx, k, max_order, L = 1e-2, 2 * math.pi / 32, 5, 2, 2
+    model = P.POLYPDE2D(dt, dx, k, max_order, "moment", "u,v", hidden_layers=L).to(cuda_device)
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for fd in model.fds:
+            fd.moment.add_((1e-2 * torch.randn(k, k, generator=g, dtype=torch.float64)).to(cuda_device))
+        model.diff_x_proj()
+        for p in model.expr_params():
+            p.copy_((0.1 * torch.randn(p.shape, generator=g, dtype=torch.float64)).to(cuda_device))
+    u0 = smooth_field(2, 2, 32, 32, 22)
+    out = model(u0.to(cuda_device), 3 * dt)
+    out.square().mean().backward()
+    model.diff_grad_proj()
+    # oracle with the same parameters
+    orders = O.order_list(max_order)
+    M = torch.stack([fd.moment.detach().cpu() for fd in model.fds]).requires_grad_(True)
+    sym = torch.stack([pl.flat_params().detach().cpu() for pl in model.polys]).requires_grad_(True)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    ref = O.rollout(u0, Ks, sym, L, dt, 3)[-1]
+    ref.square().mean().backward()
+    assert rel(out, ref) < 3e-10
+    mask = torch.stack([O.pinned_mask(k, o, "moment") for o in orders])
+    gm = torch.stack([fd.moment.grad.cpu() for fd in model.fds])
+    assert rel(gm, M.grad.masked_fill(mask, 0)) < 3e-10
+    assert (gm[mask] == 0).all()
+    # SymNet gradients arrive on the nn.Linear parameters, in the flat layout
+    gs = torch.stack([torch.cat([q.grad.reshape(-1).cpu() for q in pl.parameters()]) for pl in model.polys])
+    assert rel(gs, sym.grad) < 3e-10
+    # FD2d standalone forward == oracle single filter
+    d = model.fd01(u0.to(cuda_device))
+    K01 = O.scaled_kernels(model.fd01.moment.detach().cpu()[None], O.filter_scales([(0, 1)], dx))
+    assert rel(d, O.fd2d_apply(u0, K01).reshape(u0.shape)) < 1e-11
+
+
+# ------------------------------------------------------------------ row a12
+@pytest.mark.parametrize("k,max_order,B,H,W,steps", [(5, 4, 4, 50, 50, 20), (7, 2, 2, 33, 70, 3), (5, 2, 3, 20, 21, 2),
+                                                    (3, 1, 2, 9, 8, 2)])
+@pytest.mark.parametrize("grad_all", [False, True])
+def test_linear_rollout(P, cuda_device, k, max_order, B, H, W, steps, grad_all):
+    g = torch.Generator().manual_seed(31)
+    orders = [o for o in O.order_list(max_order) if o != (0, 0)]
+    N = len(orders)
+    dx, dt = 2 * math.pi / max(H, W), 1.5e-2 * (2 * math.pi / max(H, W)) ** 2
+    M = O.initial_moments(k, orders) + 1e-2 * torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    M0 = O.initial_moments(k, [(0, 0)]) + 1e-3 * torch.randn(1, k, k, generator=g, dtype=torch.float64)
+    K0 = O.m2k(M0)[0]
+    coe = torch.randn(N, H, W, generator=g, dtype=torch.float64)
+    u0 = smooth_field(B, 1, H, W, 32)[:, 0]
+    w = torch.randn(steps, B, H, W, generator=g, dtype=torch.float64)
+    if not grad_all:
+        w[:-1] = 0
+    leaves = [t.clone().requires_grad_(True) for t in (u0, K0, Ks, coe)]
+    ref = torch.stack(O.linear_rollout(*leaves, dt, steps))
+    (ref * w).sum().backward()
+    dl = [t.to(cuda_device).requires_grad_(True) for t in (u0, K0, Ks, coe)]
+    if grad_all:
+        out = P.linear_rollout(*dl, dt, steps)
+        (out * w.to(cuda_device)).sum().backward()
+    else:
+        out = P.linear_rollout(*dl, dt, steps, last_only=True)[None]
+        (out[0] * w[-1].to(cuda_device)).sum().backward()
+        ref = ref[-1:]
+    assert rel(out, ref) < 1e-10 * steps
+    for name, a, b in zip(["u0", "K0", "Ks", "coe"], dl, leaves):
+        assert rel(a.grad, b.grad) < 1e-10 * steps, name
+
+
+# ------------------------------------------------------------------ slab step (8e, DIST-1 on one GPU)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_slab_step_equals_periodic_step(P, cuda_device, dtype):
+    k, max_order, C, L, dx, dt = 7, 2, 2, 2, 0.1, 1e-3
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 41)
+    Ks = O.scaled_kernels(M, scales).to(cuda_device, dtype)
+    sym = sym.to(cuda_device, dtype)
+    H, W, G, halo = 96, 80, 4, 3
+    u = smooth_field(1, C, H, W, 42).to(cuda_device, dtype)
+    full = P.rollout(u, Ks, sym, L, dt, 1, last_only=True)
+    Hs = H // G
+    parts = []
+    for gidx in range(G):
+        rows = (torch.arange(-halo, Hs + halo) + gidx * Hs) % H
+        ext = u[:, :, rows.to(cuda_device)].contiguous()
+        parts.append(P.slab_step(ext, Ks, sym, L, dt, halo))
+    assert torch.equal(torch.cat(parts, dim=2), full)
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(P, cuda_device):
+    from pdenet_b200 import _lib
+    u = torch.zeros(1, 2, 8, 8, dtype=torch.float64, device=cuda_device)
+    with pytest.raises(_lib.PdenetError):  # N = 4 filters is not a full max_order bank
+        P.fd2d_features(u, torch.zeros(4, 5, 5, dtype=torch.float64, device=cuda_device))
+    with pytest.raises(RuntimeError):  # CPU tensors are refused: no CPU fallback
+        P.fd2d_features(u.cpu(), torch.zeros(6, 5, 5, dtype=torch.float64))
+    with pytest.raises(_lib.PdenetError):  # even kernel size
+        P.m2k(torch.zeros(1, 4, 4, dtype=torch.float64, device=cuda_device))
+    assert _lib.lib().pdenet_supported(8, 7, 6, 2, 2) == 1
+    assert _lib.lib().pdenet_supported(8, 9, 6, 2, 2) == 0
