@@ -148,6 +148,17 @@ PDENET_API int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels
                              int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
                              int N, int L, double dt, void *stream);
 
+/* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
+ * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
+ * 2 = reverse kernel B (data + filter gradient), 3 = small kernels (m2k, reductions).
+ * The library always counts its launches; with profiling enabled it also brackets every
+ * launch with CUDA events on the launching stream.  pdenet_profile_read synchronises those
+ * events, returns the summed milliseconds and launch counts per kind since the last read,
+ * and resets both.  Process-global, not thread-safe: a measurement aid only. */
+#define PDENET_PROF_KINDS 4
+PDENET_API int pdenet_profile_enable(int on);
+PDENET_API int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind);
+
 /* ---- measurement helper: register-only FMA loop, returns elapsed ms for `flops` flops -------
  * (used by bench.py for the CUDA-core FLOP roofline denominator). */
 PDENET_API int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream);

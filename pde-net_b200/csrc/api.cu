@@ -6,8 +6,43 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace pdenet {
+
+// ---------------------------------------------------------------------------------------------
+// measurement hooks: launch counters (always) + per-launch event pairs (when enabled)
+struct ProfRec {
+  int kind;
+  cudaEvent_t e0, e1;
+};
+struct Prof {
+  bool on = false;
+  long long launches[PDENET_PROF_KINDS] = {0, 0, 0, 0};
+  std::vector<ProfRec> recs;
+};
+static Prof g_prof;
+
+struct ProfScope {
+  ProfRec r;
+  cudaStream_t st;
+  bool live;
+  ProfScope(int kind, cudaStream_t s) : st(s), live(g_prof.on) {
+    g_prof.launches[kind]++;
+    r.kind = kind;
+    if (live) {
+      cudaEventCreate(&r.e0);
+      cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+    }
+  }
+  ~ProfScope() {
+    if (live) {
+      cudaEventRecord(r.e1, st);
+      g_prof.recs.push_back(r);
+    }
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // extern templates: the heavy kernels live in inst_<type>_k<K>.o
@@ -167,6 +202,7 @@ static int sandwich(int which, const T *in, const double *scale_host, const unsi
     const double s = scale_host ? scale_host[n] : 1.0;
     sc.s[n] = which == SW_K2M ? 1.0 / s : s;
   }
+  ProfScope ps(3, (cudaStream_t)stream);
   sandwich_kernel<T><<<N, 64, 0, (cudaStream_t)stream>>>(in, out, k, Q, sc, mask);
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -189,6 +225,7 @@ static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   const int grid = p.n_items < sms ? p.n_items : sms;
+  ProfScope ps((mode == MODE_BWD_A || mode == MODE_LIN_BWD_A) ? 1 : 0, st);
   return launch_step<T, K>(mode, N, C, VL, p, grid, st);
 }
 
@@ -207,6 +244,7 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   const int grid = p.n_items < sms ? p.n_items : sms;
+  ProfScope ps(2, st);
   return launch_adjoint<T, K>(p, grid, st);
 }
 
@@ -285,6 +323,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
   }
   if (grad_kernels) {
     const int n = N * kk;
+    ProfScope ps(3, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -427,10 +466,12 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
   }
   if (grad_kernels) {
     const int n = N * k * k;
+    ProfScope ps(3, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * Psym;
+    ProfScope ps(3, st);
     reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(symp, lay.sym_slots, n, grad_symnet);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -567,16 +608,20 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
     cur ^= 1;
   }
   const int kk = k * k;
-  if (grad_id_kernel)
+  if (grad_id_kernel) {
+    ProfScope ps(3, st);
     reduce_dk_kernel<T><<<(kk + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
+  }
   if (grad_kernels) {
     // filters 1..N: same partial layout, shifted by one filter
     const int n = N * kk;
+    ProfScope ps(3, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
                                                          grad_kernels);
   }
   if (grad_coe) {
     const size_t n = (size_t)N * img;
+    ProfScope ps(3, st);
     reduce_dcoe_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dcoe, B, n, grad_coe);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -758,6 +803,30 @@ int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const flo
                              int L, double dt, void *st) {
   return slab_step_fwd<float>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset, k,
                               N, L, dt, st);
+}
+
+int pdenet_profile_enable(int on) {
+  g_prof.on = on != 0;
+  return PDENET_OK;
+}
+int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind) {
+  double ms[PDENET_PROF_KINDS] = {0, 0, 0, 0};
+  int rc = PDENET_OK;
+  for (auto &r : g_prof.recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess)
+      rc = PDENET_E_CUDA;
+    ms[r.kind] += t;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.recs.clear();
+  for (int i = 0; i < PDENET_PROF_KINDS; ++i) {
+    if (ms_by_kind) ms_by_kind[i] = ms[i];
+    if (launches_by_kind) launches_by_kind[i] = g_prof.launches[i];
+    g_prof.launches[i] = 0;
+  }
+  return rc;
 }
 
 int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream) {

@@ -8,8 +8,8 @@ namespace pdenet {
 // (N filters, C channels) pairs compiled for the SymNet (PDE-Net 2.0) kernels: max_order 1..4
 // with up to 3 state channels, bounded by the register budget for the C*N features per point.
 #define PDENET_FOR_NC(X) X(1, 1) X(3, 1) X(3, 2) X(3, 3) X(6, 1) X(6, 2) X(6, 3) X(10, 1) X(15, 1)
-// filter counts (incl. the order-(0,0) filter) compiled for the linear (PDE-Net 1) kernels
-#define PDENET_FOR_LIN(X) X(4) X(7) X(11) X(16)
+// filter counts (incl. the order-(0,0) filter D0) compiled for the linear (PDE-Net 1) kernels: max_order 1..4
+#define PDENET_FOR_LIN(X) X(3) X(6) X(10) X(15)
 
 // returns 0 on success, -2 if (mode, N, C, VL) is not compiled, -4 on a CUDA error
 template <typename T, int K>

@@ -285,3 +285,19 @@ def fma_peak(dtype=torch.float64, iters: int = 4096):
     _lib.check(_lib.lib().pdenet_fma_peak(8 if dtype == torch.float64 else 4, iters, C.byref(flops), C.byref(ms),
                                           _stream()), "pdenet_fma_peak")
     return flops.value / (ms.value * 1e-3)
+
+
+PROFILE_KINDS = ("fwd_step", "bwd_kernel_A", "bwd_kernel_B", "small")
+
+
+def profile_enable(on: bool = True) -> None:
+    """Bracket every library launch with CUDA events (measurement aid for bench.py)."""
+    _lib.check(_lib.lib().pdenet_profile_enable(1 if on else 0), "pdenet_profile_enable")
+
+
+def profile_read():
+    """-> ({kind: summed ms}, {kind: launches}) since the last read; resets the counters."""
+    ms = (C.c_double * 4)()
+    n = (C.c_longlong * 4)()
+    _lib.check(_lib.lib().pdenet_profile_read(ms, n), "pdenet_profile_read")
+    return dict(zip(PROFILE_KINDS, list(ms))), dict(zip(PROFILE_KINDS, list(n)))

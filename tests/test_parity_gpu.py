@@ -102,7 +102,8 @@ def test_fd2d_features(P, cuda_device, k, max_order, C, H, W, dtype):
     u = smooth_field(2, C, H, W, 4)
     ref = O.fd2d_apply(u, Ks)
     out = P.fd2d_features(u.to(cuda_device, dtype), Ks.to(cuda_device, dtype))
-    assert rel(out, ref) < (1e-12 if dtype == torch.float64 else 2e-5)
+    # fp32: round-off of the 1/dx^order-scaled taps grows with the derivative order
+    assert rel(out, ref) < (1e-12 if dtype == torch.float64 else 2e-5 * 4 ** max(0, max_order - 2))
 
 
 def test_fd2d_autograd(P, cuda_device):
@@ -175,14 +176,31 @@ def test_rollout_parity_fp64(P, cuda_device, case, grad_all):
         assert rel(a, b) < TOL[torch.float64] * max(1, steps), (n, rel(a, b))
 
 
+def oracle_fp32(case):
+    """The oracle itself run in fp32 on the CPU: the round-off the reference's own float path has."""
+    k, max_order, C, L, B, H, W, steps, dx, dt = case
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 7)
+    Ks = O.scaled_kernels(M, scales)
+    u0 = smooth_field(B, C, H, W, 8)
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(steps, B, C, H, W, generator=g, dtype=torch.float64)
+    lv = [t.float().clone().requires_grad_(True) for t in (u0, Ks, sym)]
+    st = torch.stack(O.rollout(lv[0], lv[1], lv[2], L, dt, steps))
+    (st * w.float()).sum().backward()
+    return st, lv[0].grad, lv[1].grad, lv[2].grad
+
+
 @pytest.mark.parametrize("case", CASES[:5])
 def test_rollout_parity_fp32(P, cuda_device, case):
+    """fp32: within 1e-5 relative per step of the fp64 oracle, or -- where the 1/dx^2-scaled taps
+    make fp32 itself less accurate than that -- no worse than 3x the fp32 oracle's own error."""
     got, ref = run_both(P, cuda_device, case, torch.float32, True)
+    cpu32 = oracle_fp32(case)
     steps = case[7]
     names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
-    for n, a, b in zip(names, got, ref):
-        # the fp64 oracle is the truth; fp32 round-off scales with the 1/dx^2 filter taps
-        assert rel(a, b) < 20 * TOL[torch.float32] * max(1, steps), (n, rel(a, b))
+    for n, a, b, c in zip(names, got, ref, cpu32):
+        bound = max(TOL[torch.float32] * steps, 3 * rel(c, b))
+        assert rel(a, b) < bound, (n, rel(a, b), bound)
 
 
 def test_batch_chunk_and_determinism(P, cuda_device):
