@@ -150,12 +150,13 @@ PDENET_API int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels
 
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
- * 2 = reverse kernel B (data + filter gradient), 3 = small kernels (m2k, reductions).
+ * 2 = reverse kernel B1 (data gradient), 3 = reverse kernel B2 (filter gradient),
+ * 4 = small kernels (m2k, reductions).
  * The library always counts its launches; with profiling enabled it also brackets every
  * launch with CUDA events on the launching stream.  pdenet_profile_read synchronises those
  * events, returns the summed milliseconds and launch counts per kind since the last read,
  * and resets both.  Process-global, not thread-safe: a measurement aid only. */
-#define PDENET_PROF_KINDS 4
+#define PDENET_PROF_KINDS 5
 PDENET_API int pdenet_profile_enable(int on);
 PDENET_API int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind);
 

@@ -1,14 +1,18 @@
-// Second reverse kernel ("kernel B"): given the derivative adjoints g written by kernel A,
-//   lam_t(q)      = lam_{t+1}(q) [+ seed_t(q)] + sum_n sum_{a,b} K_n[a,b] * g_{c,n}(q - (a-r, b-r))
-//   dK_n[a,b]    += sum_{b,c,p} g_{c,n}(p) * u_c(p + (a-r, b-r))
+// Reverse kernels "B1" and "B2": given the derivative adjoints g written by kernel A,
+//   B1 (adjoint_kernel):      lam_t(q) = lam_{t+1}(q) [+ seed_t(q)]
+//                                        + sum_n sum_{a,b} K_n[a,b] * g_{c,n}(q - (a-r, b-r))
+//   B2 (filter_grad_kernel):  dK_n[a,b] += sum_{b,c,p} g_{c,n}(p) * u_c(p + (a-r, b-r))
 // (data gradient = transposed correlation, filter gradient =
-// global reduction).  One work item = (trajectory, channel, 64-row tile); the N filters are
-// streamed through a double-buffered cp.async pipeline (g_n tile + halo), the u tile is staged once
-// per item.  Thread micro-tile: RW=8 rows x VEC columns (16 bytes), so every shared-memory read
-// is a conflict-free LDS.128 and each loaded value feeds up to 7*VEC..7*7 FMAs from registers:
-//   B1 (data gradient):   49 flipped weights in registers, RW*VEC accumulators
-//   B2 (filter gradient): RW*VEC g values in registers, 49 accumulators, then one recursive-halving
-//                         warp reduction per (item, filter) into a per-warp global partial slot.
+// global reduction).  Thread micro-tile in both: RW=8 rows x VEC columns (16 bytes), so every
+// shared-memory read is a conflict-free LDS.128 and each loaded value feeds up to 7*VEC..7*7 FMAs
+// from registers.
+//   B1: one work item = (trajectory, channel, tile); the N filters are streamed through a
+//       double-buffered cp.async pipeline (g_n tile + halo); 49 flipped weights in registers,
+//       RW*VEC accumulators per thread.
+//   B2: warp w of a CTA owns filter n0+w for the whole launch and keeps its 49 accumulators in
+//       registers across every tile the CTA visits (the u tile + halo is staged once per item and
+//       shared by all warps; g is read straight from global memory, no halo needed), so the
+//       cross-lane reduction happens once per launch instead of once per (tile, filter).
 #pragma once
 #include "common.cuh"
 
@@ -17,8 +21,6 @@ namespace pdenet {
 template <typename T> struct AdjParams {
   const T *g; // [B][C*N][g_rows][W]
   int g_rows, g_off;
-  const T *u; // [B][C][u_rows][W]
-  int u_rows, u_off;
   int wrap_y;
   const T *lam_in; // [B][C][li_rows][W]; NULL = 0
   int li_rows, li_off;
@@ -28,7 +30,7 @@ template <typename T> struct AdjParams {
   int lo_rows, lo_off;
   const T *kernels;   // [N][K][K]
   const T *kernels0;  // if non-NULL: filter 0 is kernels0 [K][K] and `kernels` holds filters 1..N-1 (linear model)
-  double *dk_partial; // [gridDim.x * 8][N][VLB] accumulated; NULL = skip the filter gradient
+  int vec_ok;         // 1: g may be staged in 16-byte units (W % VEC == 0, base 16-byte aligned)
   int B, C, N, H, W;
   int tiles_x, tiles_y, n_items;
 };
@@ -37,8 +39,11 @@ template <typename T, int K> struct AdjCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = 256;
   static constexpr int VEC = VecOf<T>::N;
-  static constexpr int RW = 8;
+  static constexpr int RW = 16;
   static constexpr int TW = 32 * VEC, TH = RW * (NT / 32);
+  // With 16-byte staging the tile is shifted left by XS columns so that the window start
+  // (tile origin - R) is a multiple of VEC in global memory as well as in shared memory.
+  static constexpr int XS = (VEC - R % VEC) % VEC;
   static constexpr int NV = (VEC + K - 1 + VEC - 1) / VEC; // 16-byte vectors per window row
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH =
@@ -47,7 +52,7 @@ template <typename T, int K> struct AdjCfg {
   static constexpr int KKP = round_up(KK, VEC);
   static constexpr int VLB = KK <= 16 ? 16 : (KK <= 32 ? 32 : 64);
   static constexpr int TILE_ELEMS = SR * PITCH;
-  static __host__ size_t smem_bytes(int N) { return (size_t)(N * KKP + 4 * TILE_ELEMS) * sizeof(T); }
+  static __host__ size_t smem_bytes(int N) { return (size_t)(N * KKP + 2 * TILE_ELEMS) * sizeof(T); }
 };
 
 template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_kernel(const AdjParams<T> p) {
@@ -58,12 +63,10 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *wflip = reinterpret_cast<T *>(smem_raw); // [N][KKP]: wflip[n][a'*K+b'] = K_n[K-1-a'][K-1-b']
-  T *ubuf = wflip + p.N * KKP;                // [2][SR][PITCH]
-  T *gbuf = ubuf + 2 * TILE;                  // [2][SR][PITCH]
+  T *gbuf = wflip + p.N * KKP;                // [2][SR][PITCH]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, N = p.N, C = p.C;
-  const bool do_lam = p.lam_out != nullptr, do_dk = p.dk_partial != nullptr;
 
   for (int idx = tid; idx < N * KKP; idx += NT) {
     const int n = idx / KKP, e = idx % KKP;
@@ -85,24 +88,21 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
     c = t % C;
     b = t / C;
   };
-  auto stage_u = [&](int item, int ub) {
-    int b, c, ty, tx;
-    decode(item, b, c, ty, tx);
-    stage_tile_async<T, SR, SC, PITCH, NT>(ubuf + ub * TILE, p.u + (size_t)(b * C + c) * p.u_rows * W, p.u_rows,
-                                           p.u_off, p.wrap_y, ty * TH - R, tx * TW - R, H, W);
-  };
+  const int xs = p.vec_ok ? Cfg::XS : 0; // periodic in x: a shifted tiling covers the same points
   auto stage_g = [&](int item, int n, int gb) {
     int b, c, ty, tx;
     decode(item, b, c, ty, tx);
-    stage_tile_async<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W,
-                                           p.g_rows, p.g_off, p.wrap_y, ty * TH - R, tx * TW - R, H, W);
+    const T *img = p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W;
+    if (p.vec_ok)
+      stage_tile_async_vec<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
+                                                 tx * TW - xs - R, H, W);
+    else
+      stage_tile_async<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
+                                             tx * TW - R, H, W);
   };
 
-  int item = blockIdx.x, ub = 0, gb = 0;
-  if (item < p.n_items) {
-    if (do_dk) stage_u(item, 0);
-    stage_g(item, 0, 0);
-  }
+  int item = blockIdx.x, gb = 0;
+  if (item < p.n_items) stage_g(item, 0, 0);
   cp_async_commit();
 
   const int lrow = warp * RW, lcol = lane * VEC;
@@ -110,7 +110,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
   for (; item < p.n_items; item += gridDim.x) {
     int b, c, ty, tx;
     decode(item, b, c, ty, tx);
-    const int y0 = ty * TH + lrow, x0 = tx * TW + lcol;
+    const int y0 = ty * TH + lrow, x0 = tx * TW - xs + lcol; // x0 in [-xs, W - xs)
 
     T lacc[RW][VEC];
 #pragma unroll
@@ -124,7 +124,6 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
       if (n + 1 < N) {
         stage_g(item, n + 1, gb ^ 1);
       } else if (item + (int)gridDim.x < p.n_items) {
-        if (do_dk) stage_u(item + gridDim.x, ub ^ 1);
         stage_g(item + gridDim.x, 0, gb ^ 1);
       }
       cp_async_commit();
@@ -132,8 +131,6 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
       __syncthreads();
 
       const T *gs = gbuf + gb * TILE + lrow * PITCH + lcol;
-      const T *us = ubuf + ub * TILE + lrow * PITCH + lcol;
-      T gc[RW][VEC];
 
       // ---- B1: data gradient (correlation of g_n with the flipped filter)
       {
@@ -147,41 +144,6 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 #pragma unroll
           for (int v = 0; v < NV; ++v)
             ld_vec(gs + rho * PITCH + v * VEC, &row[v * VEC]);
-          if (rho >= R && rho < R + RW) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) gc[rho - R][i] = row[i + R];
-          }
-          if (do_lam) {
-#pragma unroll
-            for (int a = 0; a < K; ++a) {
-              const int j = rho - a;
-              if (j >= 0 && j < RW) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i)
-#pragma unroll
-                  for (int bb = 0; bb < K; ++bb) lacc[j][i] = fma_(wreg[a * K + bb], row[i + bb], lacc[j][i]);
-              }
-            }
-          }
-        }
-      }
-
-      // ---- B2: filter gradient
-      if (do_dk) {
-#pragma unroll
-        for (int j = 0; j < RW; ++j)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i)
-            if (!((y0 + j < H) && (x0 + i < W))) gc[j][i] = T(0);
-        T kacc[VLB];
-#pragma unroll
-        for (int e = 0; e < VLB; ++e) kacc[e] = T(0);
-#pragma unroll
-        for (int rho = 0; rho < RW + K - 1; ++rho) {
-          T row[NV * VEC];
-#pragma unroll
-          for (int v = 0; v < NV; ++v)
-            ld_vec(us + rho * PITCH + v * VEC, &row[v * VEC]);
 #pragma unroll
           for (int a = 0; a < K; ++a) {
             const int j = rho - a;
@@ -189,39 +151,27 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 #pragma unroll
               for (int i = 0; i < VEC; ++i)
 #pragma unroll
-                for (int bb = 0; bb < K; ++bb) kacc[a * K + bb] = fma_(gc[j][i], row[i + bb], kacc[a * K + bb]);
+                for (int bb = 0; bb < K; ++bb) lacc[j][i] = fma_(wreg[a * K + bb], row[i + bb], lacc[j][i]);
             }
           }
         }
-        warp_reduce_vec<T, VLB>(kacc);
-        double *slot = p.dk_partial + ((size_t)(blockIdx.x * (NT / 32) + warp) * N + n) * VLB;
-        if constexpr (VLB >= 32) {
-#pragma unroll
-          for (int i = 0; i < VLB / 32; ++i) {
-            const int e = lane * (VLB / 32) + i;
-            if (e < KK) slot[e] += (double)kacc[i];
-          }
-        } else {
-          constexpr int DUP = 32 / VLB;
-          const int e = lane / DUP;
-          if ((lane % DUP) == 0 && e < KK) slot[e] += (double)kacc[0];
-        }
       }
-      __syncthreads(); // stage buffers gb (and, on the last filter, ub) are free again
+
+      __syncthreads(); // stage buffer gb is free again
       gb ^= 1;
     }
-    ub ^= 1;
 
     // ---- item epilogue: lam_out = lam_in + seed + correlation sum
-    if (do_lam) {
+    {
 #pragma unroll
       for (int j = 0; j < RW; ++j) {
         const int y = y0 + j;
         if (y < H) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
-            const int x = x0 + i;
-            if (x < W) {
+            const int xg = x0 + i;
+            if (xg < W - xs) {
+              const int x = xg < 0 ? xg + W : xg;
               T v = lacc[j][i];
               if (p.lam_in) v += p.lam_in[((size_t)(b * C + c) * p.li_rows + (y + p.li_off)) * W + x];
               if (p.inject) v += p.inject[((size_t)(b * C + c) * p.inj_rows + (y + p.inj_off)) * W + x];
@@ -233,6 +183,172 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
     }
   }
   cp_async_wait<0>();
+}
+
+// --------------------------------------------------------------------------------------------
+template <typename T> struct FGradParams {
+  const T *g; // [B][C*N][g_rows][W]
+  int g_rows, g_off;
+  const T *u; // [B][C][u_rows][W]
+  int u_rows, u_off;
+  int wrap_y;
+  double *dk_partial; // [gridDim.x * 6][N][VLB], accumulated across launches
+  int n0, nw;         // this launch handles filters n0 .. n0+nw-1; warp w -> filter n0 + w % nw,
+                      // row part w / nw of `parts` = NWARPS / nw (nw divides NWARPS)
+  int vec_ok;         // 1 if g rows may be read with 16-byte loads (W % VEC == 0, base aligned)
+  int B, C, N, H, W;
+  int tiles_x, tiles_y, n_items;
+};
+
+template <typename T, int K> struct FGradCfg {
+  static constexpr int R = (K - 1) / 2;
+  static constexpr int VEC = VecOf<T>::N;
+  static constexpr int RW = 8;
+  static constexpr int MT = 8; // micro-tiles (of RW rows) per lane per tile
+  static constexpr int TW = 32 * VEC, TH = RW * MT;
+  static constexpr int NV = (VEC + K - 1 + VEC - 1) / VEC;
+  static constexpr int SR = TH + K - 1, SC = TW + K - 1;
+  static constexpr int PITCH =
+      round_up(SC, VEC) > (31 * VEC + NV * VEC) ? round_up(SC, VEC) : (31 * VEC + NV * VEC);
+  static constexpr int KK = K * K;
+  static constexpr int VLB = KK <= 16 ? 16 : (KK <= 32 ? 32 : 64);
+  static constexpr int TILE_ELEMS = SR * PITCH;
+  static constexpr int NT = 192; // 6 warps, 2 CTAs per SM
+  static constexpr int GST_ELEMS = 2 * RW * 32 * VEC; // per-warp double-buffered g micro-tile
+  static __host__ size_t smem_bytes() { return (size_t)(2 * TILE_ELEMS + (NT / 32) * GST_ELEMS) * sizeof(T); }
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(const FGradParams<T> p) {
+  using Cfg = FGradCfg<T, K>;
+  constexpr int NTHREADS = Cfg::NT;
+  constexpr int R = Cfg::R, VEC = Cfg::VEC, RW = Cfg::RW, MT = Cfg::MT, TW = Cfg::TW, TH = Cfg::TH;
+  constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK, VLB = Cfg::VLB;
+  constexpr int TILE = Cfg::TILE_ELEMS;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *ubuf = reinterpret_cast<T *>(smem_raw); // [2][SR][PITCH]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T *gst = ubuf + 2 * TILE + warp * Cfg::GST_ELEMS + lane * VEC; // [2][RW][32 lanes][VEC], this lane's slots
+  const int H = p.H, W = p.W, N = p.N, C = p.C;
+  const int parts = (NTHREADS / 32) / p.nw, part = warp / p.nw;
+  const int n = p.n0 + warp % p.nw;
+
+  auto decode = [&](int item, int &b, int &c, int &ty, int &tx) {
+    tx = item % p.tiles_x;
+    int t = item / p.tiles_x;
+    ty = t % p.tiles_y;
+    t /= p.tiles_y;
+    c = t % C;
+    b = t / C;
+  };
+  auto stage_u = [&](int item, int ub) {
+    int b, c, ty, tx;
+    decode(item, b, c, ty, tx);
+    stage_tile_async<T, SR, SC, PITCH, NTHREADS>(ubuf + ub * TILE, p.u + (size_t)(b * C + c) * p.u_rows * W,
+                                                 p.u_rows, p.u_off, p.wrap_y, ty * TH - R, tx * TW - R, H, W);
+  };
+
+  T kacc[VLB];
+#pragma unroll
+  for (int e = 0; e < VLB; ++e) kacc[e] = T(0);
+
+  int item = blockIdx.x, ub = 0;
+  if (item < p.n_items) stage_u(item, 0);
+  cp_async_commit();
+
+  for (; item < p.n_items; item += gridDim.x) {
+    // every cp.async group issued so far (this item's u tile, issued one item ago) has landed
+    cp_async_wait<0>();
+    __syncthreads();
+
+    {
+      int b, c, ty, tx;
+      decode(item, b, c, ty, tx);
+      const int x0 = tx * TW + lane * VEC;
+      const T *gimg = p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W;
+      const T *us = ubuf + ub * TILE + lane * VEC;
+
+      // g micro-tile: global -> this warp's staging slots (cp.async, zero-filled outside the
+      // domain), one micro-tile ahead of the compute
+      auto stage_g = [&](int mt, int gb) {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) {
+          const int y = ty * TH + mt * RW + j;
+          const bool ok = (y < H) && (x0 < W);
+          const T *grow = gimg + (size_t)((ok ? y : 0) + p.g_off) * W + (ok ? x0 : 0);
+          T *dst = gst + (gb * RW + j) * 32 * VEC;
+          if (p.vec_ok) {
+            cp_async_16_zfill(dst, grow, ok);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dst[i] = (ok && x0 + i < W) ? grow[i] : T(0);
+          }
+        }
+      };
+
+      // group order per item: G(first), U(next item), G(second), G(third), ...  so the next
+      // item's u tile never sits in front of the g micro-tile the warp is about to consume
+      int gb = 0;
+      stage_g(part, 0);
+      cp_async_commit();
+      if (item + (int)gridDim.x < p.n_items) stage_u(item + gridDim.x, ub ^ 1);
+      cp_async_commit();
+      bool first = true;
+#pragma unroll 1
+      for (int mt = part; mt < MT; mt += parts) {
+        if (ty * TH + mt * RW >= H) break; // warp-uniform: nothing left in this tile
+        if (mt + parts < MT) stage_g(mt + parts, gb ^ 1);
+        cp_async_commit();
+        if (first)
+          cp_async_wait<2>();
+        else
+          cp_async_wait<1>();
+        first = false;
+        T gc[RW][VEC];
+#pragma unroll
+        for (int j = 0; j < RW; ++j) ld_vec(gst + (gb * RW + j) * 32 * VEC, &gc[j][0]);
+        const T *um = us + mt * RW * PITCH;
+#pragma unroll
+        for (int rho = 0; rho < RW + K - 1; ++rho) {
+          T row[NV * VEC];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) ld_vec(um + rho * PITCH + v * VEC, &row[v * VEC]);
+#pragma unroll
+          for (int a = 0; a < K; ++a) {
+            const int j = rho - a;
+            if (j >= 0 && j < RW) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i)
+#pragma unroll
+                for (int bb = 0; bb < K; ++bb) kacc[a * K + bb] = fma_(gc[j][i], row[i + bb], kacc[a * K + bb]);
+            }
+          }
+        }
+        gb ^= 1;
+      }
+    }
+    __syncthreads(); // the u tile in `ub` is free again
+    ub ^= 1;
+  }
+  cp_async_wait<0>();
+
+  {
+    warp_reduce_vec<T, VLB>(kacc);
+    double *slot = p.dk_partial + ((size_t)(blockIdx.x * (NTHREADS / 32) + part) * N + n) * VLB;
+    if constexpr (VLB >= 32) {
+#pragma unroll
+      for (int i = 0; i < VLB / 32; ++i) {
+        const int e = lane * (VLB / 32) + i;
+        if (e < KK) slot[e] += (double)kacc[i];
+      }
+    } else {
+      constexpr int DUP = 32 / VLB;
+      const int e = lane / DUP;
+      if ((lane % DUP) == 0 && e < KK) slot[e] += (double)kacc[0];
+    }
+  }
 }
 
 // ---- tiny deterministic finishing kernels ----------------------------------------------------

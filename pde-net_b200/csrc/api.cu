@@ -18,7 +18,7 @@ struct ProfRec {
 };
 struct Prof {
   bool on = false;
-  long long launches[PDENET_PROF_KINDS] = {0, 0, 0, 0};
+  long long launches[PDENET_PROF_KINDS] = {0, 0, 0, 0, 0};
   std::vector<ProfRec> recs;
 };
 static Prof g_prof;
@@ -49,6 +49,8 @@ struct ProfScope {
 #define PDENET_EXTERN(TT, KK)                                                                                     \
   extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
   extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, cudaStream_t);                          \
+  extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, cudaStream_t);                    \
+  extern template void filter_grad_tile<TT, KK>(int &, int &);                                                   \
   extern template int adjoint_vlb<TT, KK>();                                                                     \
   extern template void step_tile<TT, KK>(int &, int &);                                                          \
   extern template void adjoint_tile<TT, KK>(int &, int &);
@@ -202,7 +204,7 @@ static int sandwich(int which, const T *in, const double *scale_host, const unsi
     const double s = scale_host ? scale_host[n] : 1.0;
     sc.s[n] = which == SW_K2M ? 1.0 / s : s;
   }
-  ProfScope ps(3, (cudaStream_t)stream);
+  ProfScope ps(4, (cudaStream_t)stream);
   sandwich_kernel<T><<<N, 64, 0, (cudaStream_t)stream>>>(in, out, k, Q, sc, mask);
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -241,11 +243,51 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.n_items = B * C * p.tiles_x * p.tiles_y;
+  const int vec = 16 / (int)sizeof(T);
+  p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   const int grid = p.n_items < sms ? p.n_items : sms;
   ProfScope ps(2, st);
   return launch_adjoint<T, K>(p, grid, st);
+}
+
+// Filter gradient: warps own filters; N filters are covered by launches of nw in {6, 3, 2, 1}
+// filters each (nw divides the 6 warps of a CTA; the other warps split the tile rows).
+constexpr int kFGradWarps = 6;
+constexpr int kFGradCtasPerSm = 2;
+static int dk_slot_count(int sms) { return sms * kFGradCtasPerSm * kFGradWarps; }
+
+template <typename T, int K>
+static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W, cudaStream_t st) {
+  int tw, th;
+  filter_grad_tile<T, K>(tw, th);
+  p.B = B;
+  p.C = C;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
+  p.n_items = B * C * p.tiles_x * p.tiles_y;
+  const int vec = 16 / (int)sizeof(T);
+  p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const int cap = sms * kFGradCtasPerSm;
+  const int grid = p.n_items < cap ? p.n_items : cap;
+  int n0 = 0;
+  while (n0 < N) {
+    const int left = N - n0;
+    const int nw = left >= 6 ? 6 : (left >= 3 ? 3 : (left >= 2 ? 2 : 1));
+    p.n0 = n0;
+    p.nw = nw;
+    ProfScope ps(3, st);
+    const int rc = launch_filter_grad<T, K>(p, grid, st);
+    if (rc) return rc;
+    n0 += nw;
+  }
+  return 0;
 }
 
 // ---- forward rollout (rows a5-a10) -----------------------------------------------------------
@@ -299,7 +341,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
     return PDENET_E_BADARG;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64), slots = sms * 8;
+  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64), slots = dk_slot_count(sms);
   const size_t need = (size_t)slots * N * vlb * sizeof(double);
   if (ws_bytes < need) return PDENET_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -309,21 +351,28 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
   memset(&q, 0, sizeof(q));
   q.g = grad_feats;
   q.g_rows = H;
-  q.u = u;
-  q.u_rows = H;
   q.wrap_y = 1;
   q.lam_out = grad_u;
   q.lo_rows = H;
   q.kernels = kernels;
-  q.dk_partial = grad_kernels ? dkp : nullptr;
   int rc = 0;
-  if (grad_u || grad_kernels) {
+  if (grad_u) {
     PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, C, N, H, W, st)));
     if (rc) return rc;
   }
   if (grad_kernels) {
+    FGradParams<T> f;
+    memset(&f, 0, sizeof(f));
+    f.g = grad_feats;
+    f.g_rows = H;
+    f.u = u;
+    f.u_rows = H;
+    f.wrap_y = 1;
+    f.dk_partial = dkp;
+    PDENET_DISPATCH_K(k, rc = (run_filter_grad<T, KK_>(f, B, C, N, H, W, st)));
+    if (rc) return rc;
     const int n = N * kk;
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -366,7 +415,7 @@ static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N,
   l.chunk = (batch_chunk <= 0 || batch_chunk > B) ? B : batch_chunk;
   const int kk = k * k;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  l.dk_slots = sms * 8;
+  l.dk_slots = dk_slot_count(sms);
   l.sym_slots = sms;
   const size_t img = (size_t)H * W;
   size_t o = 0;
@@ -419,7 +468,6 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
     const T *ut = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
     T *lam_out = t == 0 ? grad_u0 : lamb[cur];
     const T *inject = (grad_mode == PDENET_GRAD_ALL && t > 0) ? grad_states + (size_t)(t - 1) * stride : nullptr;
-    const bool need_b = lam_out != nullptr || grad_kernels != nullptr;
     for (int b0 = 0; b0 < B; b0 += lay.chunk) {
       const int nb = (B - b0) < lay.chunk ? (B - b0) : lay.chunk;
       const size_t boff = (size_t)b0 * C * img;
@@ -441,24 +489,34 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
       int rc = 0;
       PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
       if (rc) return rc;
-      if (!need_b) continue;
-      AdjParams<T> q;
-      memset(&q, 0, sizeof(q));
-      q.g = gbuf;
-      q.g_rows = H;
-      q.u = ut + boff;
-      q.u_rows = H;
-      q.wrap_y = 1;
-      q.lam_in = lam_in + boff;
-      q.li_rows = H;
-      q.inject = inject ? inject + boff : nullptr;
-      q.inj_rows = H;
-      q.lam_out = lam_out ? lam_out + boff : nullptr;
-      q.lo_rows = H;
-      q.kernels = kernels;
-      q.dk_partial = grad_kernels ? dkp : nullptr;
-      PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, nb, C, N, H, W, st)));
-      if (rc) return rc;
+      if (lam_out) {
+        AdjParams<T> q;
+        memset(&q, 0, sizeof(q));
+        q.g = gbuf;
+        q.g_rows = H;
+        q.wrap_y = 1;
+        q.lam_in = lam_in + boff;
+        q.li_rows = H;
+        q.inject = inject ? inject + boff : nullptr;
+        q.inj_rows = H;
+        q.lam_out = lam_out + boff;
+        q.lo_rows = H;
+        q.kernels = kernels;
+        PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, nb, C, N, H, W, st)));
+        if (rc) return rc;
+      }
+      if (grad_kernels) {
+        FGradParams<T> f;
+        memset(&f, 0, sizeof(f));
+        f.g = gbuf;
+        f.g_rows = H;
+        f.u = ut + boff;
+        f.u_rows = H;
+        f.wrap_y = 1;
+        f.dk_partial = dkp;
+        PDENET_DISPATCH_K(k, rc = (run_filter_grad<T, KK_>(f, nb, C, N, H, W, st)));
+        if (rc) return rc;
+      }
     }
     lam_in = lam_out;
     cur ^= 1;
@@ -466,12 +524,12 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
   }
   if (grad_kernels) {
     const int n = N * k * k;
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * Psym;
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(symp, lay.sym_slots, n, grad_symnet);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -511,7 +569,7 @@ static LinLayout lin_layout(size_t es, int B, int H, int W, int k, int N, int sm
   LinLayout l;
   const int kk = k * k;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  l.dk_slots = sms * 8;
+  l.dk_slots = dk_slot_count(sms);
   const size_t img = (size_t)H * W;
   size_t o = 0;
   l.off_g = o;
@@ -585,13 +643,11 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
     int rc = 0;
     PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_LIN_BWD_A, N + 1, 1, 16, p, B, H, W, st)));
     if (rc) return rc;
-    if (lam_out || want_dk) {
+    if (lam_out) {
       AdjParams<T> q;
       memset(&q, 0, sizeof(q));
       q.g = gbuf;
       q.g_rows = H;
-      q.u = ut;
-      q.u_rows = H;
       q.wrap_y = 1;
       q.lam_in = nullptr; // the D0 filter carries the identity path
       q.inject = inject;
@@ -600,8 +656,19 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
       q.lo_rows = H;
       q.kernels = kernels;
       q.kernels0 = id_kernel;
-      q.dk_partial = want_dk ? dkp : nullptr;
       PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, 1, N + 1, H, W, st)));
+      if (rc) return rc;
+    }
+    if (want_dk) {
+      FGradParams<T> f;
+      memset(&f, 0, sizeof(f));
+      f.g = gbuf;
+      f.g_rows = H;
+      f.u = ut;
+      f.u_rows = H;
+      f.wrap_y = 1;
+      f.dk_partial = dkp;
+      PDENET_DISPATCH_K(k, rc = (run_filter_grad<T, KK_>(f, B, 1, N + 1, H, W, st)));
       if (rc) return rc;
     }
     lam_in = lam_out;
@@ -609,19 +676,19 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   }
   const int kk = k * k;
   if (grad_id_kernel) {
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_dk_kernel<T><<<(kk + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
   }
   if (grad_kernels) {
     // filters 1..N: same partial layout, shifted by one filter
     const int n = N * kk;
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
                                                          grad_kernels);
   }
   if (grad_coe) {
     const size_t n = (size_t)N * img;
-    ProfScope ps(3, st);
+    ProfScope ps(4, st);
     reduce_dcoe_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dcoe, B, n, grad_coe);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
@@ -713,7 +780,7 @@ size_t pdenet_fd2d_bwd_workspace_bytes(int k, int N) {
   const int sms = sm_count();
   if (sms <= 0 || k <= 0 || N <= 0) return 0;
   const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  return (size_t)sms * 8 * N * vlb * sizeof(double);
+  return (size_t)dk_slot_count(sms) * N * vlb * sizeof(double);
 }
 int pdenet_fd2d_bwd_f64(const double *u, const double *grad_feats, const double *kernels, double *grad_u,
                         double *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,
@@ -810,7 +877,7 @@ int pdenet_profile_enable(int on) {
   return PDENET_OK;
 }
 int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind) {
-  double ms[PDENET_PROF_KINDS] = {0, 0, 0, 0};
+  double ms[PDENET_PROF_KINDS] = {0, 0, 0, 0, 0};
   int rc = PDENET_OK;
   for (auto &r : g_prof.recs) {
     float t = 0.f;

@@ -54,6 +54,12 @@ __device__ __forceinline__ void cp_async_elem(float *smem, const float *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
+// 16-byte copy, zero-filled when !valid (src-size 0); streams past L1
+__device__ __forceinline__ void cp_async_16_zfill(void *smem, const void *gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
@@ -82,6 +88,34 @@ __device__ __forceinline__ void stage_tile_async(T *dst, const T *__restrict__ i
     for (int j = 0; j < NCB; ++j) {
       const int lx = lane + 32 * j;
       if (lx < COLS) cp_async_elem(drow + lx, srow + gx[j]);
+    }
+  }
+}
+
+// Same window, staged in 16-byte units.  Requires x0 % VEC == 0, W % VEC == 0, a 16-byte aligned
+// image base and PITCH % VEC == 0; may stage up to VEC-1 columns past COLS (still inside PITCH).
+template <typename T, int ROWS, int COLS, int PITCH, int NT>
+__device__ __forceinline__ void stage_tile_async_vec(T *dst, const T *__restrict__ img, int rows_buf, int row_off,
+                                                     int wrap_y, int y0, int x0, int H, int W) {
+  constexpr int VEC = VecOf<T>::N;
+  constexpr int UNITS = (COLS + VEC - 1) / VEC;
+  static_assert(UNITS * VEC <= PITCH && PITCH % VEC == 0, "pitch too small for vector staging");
+  constexpr int NCB = (UNITS + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int gx[NCB];
+#pragma unroll
+  for (int j = 0; j < NCB; ++j) gx[j] = wrap_index(x0 + (lane + 32 * j) * VEC, W);
+  for (int row = warp; row < ROWS; row += NT / 32) {
+    int gy = y0 + row;
+    if (wrap_y) gy = wrap_index(gy, H);
+    gy += row_off;
+    gy = gy < 0 ? 0 : (gy >= rows_buf ? rows_buf - 1 : gy);
+    const T *srow = img + (size_t)gy * W;
+    T *drow = dst + row * PITCH;
+#pragma unroll
+    for (int j = 0; j < NCB; ++j) {
+      const int u = lane + 32 * j;
+      if (u < UNITS) cp_async_16_zfill(drow + u * VEC, srow + gx[j], true);
     }
   }
 }

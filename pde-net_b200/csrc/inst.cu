@@ -56,6 +56,19 @@ template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid,
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st) {
+  using Cfg = FGradCfg<T, K>;
+  const size_t smem = Cfg::smem_bytes();
+  auto kern = filter_grad_kernel<T, K>;
+  if (allow_smem(kern, smem) != 0) return -4;
+  kern<<<grid, Cfg::NT, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+template <typename T, int K> void filter_grad_tile(int &tw, int &th) {
+  tw = FGradCfg<T, K>::TW;
+  th = FGradCfg<T, K>::TH;
+}
+
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
 template <typename T, int K> void step_tile(int &tw, int &th) {
   tw = StepCfg<T, K, 3, 1>::TW;
@@ -68,6 +81,8 @@ template <typename T, int K> void adjoint_tile(int &tw, int &th) {
 
 template int launch_step<PDENET_T, PDENET_K>(int, int, int, int, const StepParams<PDENET_T> &, int, cudaStream_t);
 template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int, cudaStream_t);
+template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, cudaStream_t);
+template void filter_grad_tile<PDENET_T, PDENET_K>(int &, int &);
 template int adjoint_vlb<PDENET_T, PDENET_K>();
 template void step_tile<PDENET_T, PDENET_K>(int &, int &);
 template void adjoint_tile<PDENET_T, PDENET_K>(int &, int &);

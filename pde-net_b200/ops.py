@@ -287,7 +287,7 @@ def fma_peak(dtype=torch.float64, iters: int = 4096):
     return flops.value / (ms.value * 1e-3)
 
 
-PROFILE_KINDS = ("fwd_step", "bwd_kernel_A", "bwd_kernel_B", "small")
+PROFILE_KINDS = ("fwd_step", "bwd_kernel_A", "bwd_kernel_B1", "bwd_kernel_B2", "small")
 
 
 def profile_enable(on: bool = True) -> None:
@@ -297,7 +297,7 @@ def profile_enable(on: bool = True) -> None:
 
 def profile_read():
     """-> ({kind: summed ms}, {kind: launches}) since the last read; resets the counters."""
-    ms = (C.c_double * 4)()
-    n = (C.c_longlong * 4)()
+    ms = (C.c_double * len(PROFILE_KINDS))()
+    n = (C.c_longlong * len(PROFILE_KINDS))()
     _lib.check(_lib.lib().pdenet_profile_read(ms, n), "pdenet_profile_read")
     return dict(zip(PROFILE_KINDS, list(ms))), dict(zip(PROFILE_KINDS, list(n)))
