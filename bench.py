@@ -244,8 +244,8 @@ def run_ours(args):
     host_u0.copy_(u0)
     stage = torch.empty_like(u0)
     nparam = sum(p.numel() for p in params)
-    flat_grad = torch.zeros(nparam + 1, dtype=dtype, device=dev)  # grads + loss, one all-reduce
     host_out = torch.empty(nparam + 1, dtype=dtype, pin_memory=True)
+    from pdenet_b200 import parallel
 
     def one_pass(inp):
         for p in params:
@@ -254,19 +254,17 @@ def run_ours(args):
         loss = out.square().mean() / world
         loss.backward()
         model.diff_grad_proj()
-        o = 0
-        for p in params:
-            flat_grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
-            o += p.numel()
-        flat_grad[nparam] = loss.detach()
-        if world > 1:
-            dist.all_reduce(flat_grad)
-        return flat_grad
+        # one flat all-reduce of every gradient + the loss (no-op at world == 1)
+        return parallel.allreduce_gradients(params, loss=loss.detach())
 
     def one_pass_e2e():
         stage.copy_(host_u0, non_blocking=True)          # H2D of this pass's inputs (pinned)
-        fg = one_pass(stage)
-        host_out.copy_(fg, non_blocking=True)            # D2H of loss + gradients
+        total = one_pass(stage)
+        o = 0
+        for p in params:                                  # D2H of the gradients + loss
+            host_out[o:o + p.numel()].copy_(p.grad.reshape(-1), non_blocking=True)
+            o += p.numel()
+        host_out[nparam:].copy_(total.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return host_out
 

@@ -59,7 +59,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
   using Cfg = AdjCfg<T, K>;
   constexpr int R = Cfg::R, NT = Cfg::NT, VEC = Cfg::VEC, RW = Cfg::RW, TW = Cfg::TW, TH = Cfg::TH;
   constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK, KKP = Cfg::KKP;
-  constexpr int VLB = Cfg::VLB, TILE = Cfg::TILE_ELEMS;
+  constexpr int TILE = Cfg::TILE_ELEMS;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *wflip = reinterpret_cast<T *>(smem_raw); // [N][KKP]: wflip[n][a'*K+b'] = K_n[K-1-a'][K-1-b']
@@ -144,16 +144,17 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 #pragma unroll
           for (int v = 0; v < NV; ++v)
             ld_vec(gs + rho * PITCH + v * VEC, &row[v * VEC]);
+          // tap column outermost: consecutive FMAs hit different accumulators (no dependent chains)
 #pragma unroll
-          for (int a = 0; a < K; ++a) {
-            const int j = rho - a;
-            if (j >= 0 && j < RW) {
+          for (int bb = 0; bb < K; ++bb)
 #pragma unroll
-              for (int i = 0; i < VEC; ++i)
+            for (int a = 0; a < K; ++a) {
+              const int j = rho - a;
+              if (j >= 0 && j < RW) {
 #pragma unroll
-                for (int bb = 0; bb < K; ++bb) lacc[j][i] = fma_(wreg[a * K + bb], row[i + bb], lacc[j][i]);
+                for (int i = 0; i < VEC; ++i) lacc[j][i] = fma_(wreg[a * K + bb], row[i + bb], lacc[j][i]);
+              }
             }
-          }
         }
       }
 
@@ -161,24 +162,36 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
       gb ^= 1;
     }
 
-    // ---- item epilogue: lam_out = lam_in + seed + correlation sum
+    // ---- item epilogue: lam_out = lam_in + seed + correlation sum.  Loads are issued for a
+    // whole row group before any use (clamped addresses instead of branches) so they overlap.
     {
+      const size_t img = (size_t)(b * C + c);
 #pragma unroll
-      for (int j = 0; j < RW; ++j) {
-        const int y = y0 + j;
-        if (y < H) {
+      for (int j0 = 0; j0 < RW; j0 += 4) {
+        T add[4][VEC];
+        bool ok[4][VEC];
+        int xx[4][VEC];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int y = y0 + j0 + jj;
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
             const int xg = x0 + i;
-            if (xg < W - xs) {
-              const int x = xg < 0 ? xg + W : xg;
-              T v = lacc[j][i];
-              if (p.lam_in) v += p.lam_in[((size_t)(b * C + c) * p.li_rows + (y + p.li_off)) * W + x];
-              if (p.inject) v += p.inject[((size_t)(b * C + c) * p.inj_rows + (y + p.inj_off)) * W + x];
-              p.lam_out[((size_t)(b * C + c) * p.lo_rows + (y + p.lo_off)) * W + x] = v;
-            }
+            ok[jj][i] = (y < H) && (xg < W - xs);
+            xx[jj][i] = xg < 0 ? xg + W : xg;
+            const int ys = ok[jj][i] ? y : 0, xc = ok[jj][i] ? xx[jj][i] : 0;
+            T v = T(0);
+            if (p.lam_in) v = p.lam_in[(img * p.li_rows + (ys + p.li_off)) * W + xc];
+            if (p.inject) v += p.inject[(img * p.inj_rows + (ys + p.inj_off)) * W + xc];
+            add[jj][i] = v;
           }
         }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+          for (int i = 0; i < VEC; ++i)
+            if (ok[jj][i])
+              p.lam_out[(img * p.lo_rows + (y0 + j0 + jj + p.lo_off)) * W + xx[jj][i]] = lacc[j0 + jj][i] + add[jj][i];
       }
     }
   }
@@ -204,7 +217,7 @@ template <typename T, int K> struct FGradCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int VEC = VecOf<T>::N;
   static constexpr int RW = 8;
-  static constexpr int MT = 8; // micro-tiles (of RW rows) per lane per tile
+  static constexpr int MT = 4; // micro-tiles (of RW rows) per lane per tile (2 CTAs/SM fit in shared memory)
   static constexpr int TW = 32 * VEC, TH = RW * MT;
   static constexpr int NV = (VEC + K - 1 + VEC - 1) / VEC;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;

@@ -52,7 +52,6 @@ struct ProfScope {
   extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, cudaStream_t);                    \
   extern template void filter_grad_tile<TT, KK>(int &, int &);                                                   \
   extern template int adjoint_vlb<TT, KK>();                                                                     \
-  extern template void step_tile<TT, KK>(int &, int &);                                                          \
   extern template void adjoint_tile<TT, KK>(int &, int &);
 PDENET_EXTERN(double, 3) PDENET_EXTERN(double, 5) PDENET_EXTERN(double, 7)
 PDENET_EXTERN(float, 3) PDENET_EXTERN(float, 5) PDENET_EXTERN(float, 7)
@@ -216,19 +215,13 @@ static bool bad_geom(int B, int C, int H, int W, int k, int N) {
 
 template <typename T, int K>
 static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int H, int W, cudaStream_t st) {
-  int tw, th;
-  step_tile<T, K>(tw, th);
   p.B = B;
   p.H = H;
   p.W = W;
-  p.tiles_x = (W + tw - 1) / tw;
-  p.tiles_y = (H + th - 1) / th;
-  p.n_items = B * p.tiles_x * p.tiles_y;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  const int grid = p.n_items < sms ? p.n_items : sms;
   ProfScope ps((mode == MODE_BWD_A || mode == MODE_LIN_BWD_A) ? 1 : 0, st);
-  return launch_step<T, K>(mode, N, C, VL, p, grid, st);
+  return launch_step<T, K>(mode, N, C, VL, p, sms, st);
 }
 
 template <typename T, int K>

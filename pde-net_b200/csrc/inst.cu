@@ -13,8 +13,13 @@ template <typename KernelT> static int allow_smem(KernelT kern, size_t smem) {
 }
 
 template <typename T, int K, int N, int C, int MODE, int VL>
-static int launch_step_one(const StepParams<T> &p, int grid, cudaStream_t st) {
-  using Cfg = StepCfg<T, K, N, C>;
+static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
+  using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
+  StepParams<T> p = p_in;
+  p.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
+  p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
+  p.n_items = p.B * p.tiles_x * p.tiles_y;
+  const int grid = p.n_items < sms ? p.n_items : sms;
   const size_t smem = Cfg::smem_bytes(p.Psym, MODE == MODE_BWD_A);
   auto kern = step_kernel<T, K, N, C, MODE, VL>;
   if (allow_smem(kern, smem) != 0) return -4;
@@ -23,23 +28,23 @@ static int launch_step_one(const StepParams<T> &p, int grid, cudaStream_t st) {
 }
 
 template <typename T, int K>
-int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int grid, cudaStream_t st) {
+int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st) {
 #define PDENET_CASE(NN, CC)                                                                                       \
   if (N == NN && C == CC) {                                                                                      \
-    if (mode == MODE_FWD) return launch_step_one<T, K, NN, CC, MODE_FWD, 16>(p, grid, st);                       \
-    if (mode == MODE_FEATS) return launch_step_one<T, K, NN, CC, MODE_FEATS, 16>(p, grid, st);                   \
+    if (mode == MODE_FWD) return launch_step_one<T, K, NN, CC, MODE_FWD, 16>(p, sms, st);                       \
+    if (mode == MODE_FEATS) return launch_step_one<T, K, NN, CC, MODE_FEATS, 16>(p, sms, st);                   \
     if (mode == MODE_BWD_A) {                                                                                    \
       if constexpr (NN * CC + 1 < 16)                                                                            \
-        if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, grid, st);                         \
-      if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, grid, st);                           \
+        if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, sms, st);                         \
+      if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, sms, st);                           \
     }                                                                                                            \
   }
   PDENET_FOR_NC(PDENET_CASE)
 #undef PDENET_CASE
 #define PDENET_CASE(NN)                                                                                           \
   if (N == NN && C == 1) {                                                                                       \
-    if (mode == MODE_LIN_FWD) return launch_step_one<T, K, NN, 1, MODE_LIN_FWD, 16>(p, grid, st);                \
-    if (mode == MODE_LIN_BWD_A) return launch_step_one<T, K, NN, 1, MODE_LIN_BWD_A, 16>(p, grid, st);            \
+    if (mode == MODE_LIN_FWD) return launch_step_one<T, K, NN, 1, MODE_LIN_FWD, 16>(p, sms, st);                \
+    if (mode == MODE_LIN_BWD_A) return launch_step_one<T, K, NN, 1, MODE_LIN_BWD_A, 16>(p, sms, st);            \
   }
   PDENET_FOR_LIN(PDENET_CASE)
 #undef PDENET_CASE
@@ -70,10 +75,6 @@ template <typename T, int K> void filter_grad_tile(int &tw, int &th) {
 }
 
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
-template <typename T, int K> void step_tile(int &tw, int &th) {
-  tw = StepCfg<T, K, 3, 1>::TW;
-  th = StepCfg<T, K, 3, 1>::TH;
-}
 template <typename T, int K> void adjoint_tile(int &tw, int &th) {
   tw = AdjCfg<T, K>::TW;
   th = AdjCfg<T, K>::TH;
@@ -84,7 +85,6 @@ template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int
 template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, cudaStream_t);
 template void filter_grad_tile<PDENET_T, PDENET_K>(int &, int &);
 template int adjoint_vlb<PDENET_T, PDENET_K>();
-template void step_tile<PDENET_T, PDENET_K>(int &, int &);
 template void adjoint_tile<PDENET_T, PDENET_K>(int &, int &);
 
 } // namespace pdenet

@@ -11,14 +11,14 @@ namespace pdenet {
 // filter counts (incl. the order-(0,0) filter D0) compiled for the linear (PDE-Net 1) kernels: max_order 1..4
 #define PDENET_FOR_LIN(X) X(3) X(6) X(10) X(15)
 
-// returns 0 on success, -2 if (mode, N, C, VL) is not compiled, -4 on a CUDA error
+// returns 0 on success, -2 if (mode, N, C, VL) is not compiled, -4 on a CUDA error; fills the
+// tile decomposition from p.B/H/W and launches min(items, sms) persistent CTAs
 template <typename T, int K>
-int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int grid, cudaStream_t st);
+int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st);
 template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st);
 template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st);
 template <typename T, int K> void filter_grad_tile(int &tw, int &th);
 template <typename T, int K> int adjoint_vlb();
-template <typename T, int K> void step_tile(int &tw, int &th);
 template <typename T, int K> void adjoint_tile(int &tw, int &th);
 
 } // namespace pdenet

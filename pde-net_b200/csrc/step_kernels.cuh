@@ -44,10 +44,17 @@ template <typename T> struct TransposeCfg {
   static constexpr int ELEMS = 32 * PITCH;
 };
 
-template <typename T, int K, int N, int C> struct StepCfg {
+// Threads per CTA: the forward-type kernels fit 168 registers when C*N <= 12, so they run 12
+// warps per SM; the reverse kernel A (and the widest banks) need up to 255 registers -> 8 warps.
+__host__ __device__ constexpr int step_threads(int mode, int M) {
+  return ((mode == MODE_FWD || mode == MODE_FEATS || mode == MODE_LIN_FWD) && M <= 12) ? 384 : 256;
+}
+
+template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
-  static constexpr int NT = 256;
-  static constexpr int TW = 64, TH = 32, P = 4;
+  static constexpr int NT = NT_;
+  static constexpr int P = 4;
+  static constexpr int TW = 64, TH = (NT / 64) * 2 * P; // 2 warps across, NT/64 down, 2 strips of P rows each
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH = SC;
   static constexpr int VEC = VecOf<T>::N;
@@ -303,8 +310,8 @@ __device__ __forceinline__ void reverse_half(const T (&d)[M][P], const T *syms, 
 
 // --------------------------------------------------------------------------------------------
 template <typename T, int K, int N, int C, int MODE, int VL>
-__global__ void __launch_bounds__(256, 1) step_kernel(const StepParams<T> p) {
-  using Cfg = StepCfg<T, K, N, C>;
+__global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const StepParams<T> p) {
+  using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, NP = Cfg::NP, M = Cfg::M, NT = Cfg::NT, VEC = Cfg::VEC;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
@@ -366,8 +373,8 @@ __global__ void __launch_bounds__(256, 1) step_kernel(const StepParams<T> p) {
     const int x = tx * TW + col;
 
 #pragma unroll 1
-    for (int s = 0; s < TH / (4 * P); ++s) {
-      const int row0 = (wy * (TH / (4 * P)) + s) * P;
+    for (int s = 0; s < TH / ((NT / 64) * P); ++s) {
+      const int row0 = (wy * (TH / ((NT / 64) * P)) + s) * P;
       const int y0 = ty * TH + row0;
       bool valid[P];
 #pragma unroll

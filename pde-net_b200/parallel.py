@@ -1,0 +1,113 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed.
+
+* Batch sharding (config 4): trajectories are independent, so each rank runs the fused rollout on
+  its shard and the only exchange is ONE all-reduce of a single flat buffer holding every
+  moment / SymNet gradient (plus the loss) -- a few KB, latency-bound over NVLink/NVSwitch.
+* Slab domain decomposition (config 5): rows of one huge grid are split across ranks; before each
+  step every rank fills its ghost rows from its ring neighbours (periodic in H makes it a true
+  ring) and calls the non-periodic slab step of the C-ABI.  Forward only in this round.
+
+The reference is single-process: nothing here replaces a reference interface.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard ``(start, count)`` of ``total`` items for ``rank``; sizes differ by <= 1."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def flat_allreduce(tensors: Sequence[torch.Tensor], group=None, extra: Optional[torch.Tensor] = None):
+    """Sum ``tensors`` (and the optional scalar ``extra``) across ranks through ONE flat buffer
+    and write the result back in place.  Returns the reduced ``extra`` (or None)."""
+    tensors = [t for t in tensors if t is not None]
+    n = sum(t.numel() for t in tensors)
+    ref = tensors[0] if tensors else extra
+    flat = torch.empty(n + (1 if extra is not None else 0), dtype=ref.dtype, device=ref.device)
+    o = 0
+    for t in tensors:
+        flat[o:o + t.numel()].copy_(t.reshape(-1))
+        o += t.numel()
+    if extra is not None:
+        flat[n] = extra
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, group=group)
+    o = 0
+    for t in tensors:
+        t.copy_(flat[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
+    return flat[n] if extra is not None else None
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, loss: Optional[torch.Tensor] = None):
+    """Data-parallel gradient exchange: one all-reduce for every ``.grad`` (and the loss)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    return flat_allreduce(grads, group=group, extra=loss)
+
+
+class SlabDecomposition:
+    """Rows ``[row0, row0+Hs)`` of an H-row periodic grid live on this rank; ``halo`` ghost rows on
+    each side are filled from the ring neighbours before every step."""
+
+    def __init__(self, H: int, halo: int, rank: int, world: int, group=None):
+        if H % world:
+            raise ValueError("H must divide evenly over the ranks")
+        self.H, self.halo, self.rank, self.world, self.group = H, halo, rank, world, group
+        self.Hs = H // world
+        if self.Hs < halo:
+            raise ValueError("slab thinner than the halo")
+        self.row0 = rank * self.Hs
+        self.up = (rank - 1) % world      # owns the rows above (smaller y)
+        self.down = (rank + 1) % world    # owns the rows below
+
+    def extend(self, u_local: torch.Tensor) -> torch.Tensor:
+        """[B,C,Hs,W] -> [B,C,Hs+2*halo,W] with the interior copied in (ghosts unset)."""
+        B, C, Hs, W = u_local.shape
+        ext = torch.empty(B, C, Hs + 2 * self.halo, W, dtype=u_local.dtype, device=u_local.device)
+        ext[:, :, self.halo:self.halo + Hs] = u_local
+        return ext
+
+    def exchange(self, ext: torch.Tensor) -> None:
+        """Fill the ghost rows of ``ext`` in place: top ghosts <- bottom rows of `up`, bottom
+        ghosts <- top rows of `down`.  One batched isend/irecv per neighbour."""
+        h, Hs = self.halo, self.Hs
+        top_rows = ext[:, :, h:2 * h].contiguous()            # my first rows -> `up`'s bottom ghosts
+        bot_rows = ext[:, :, Hs:Hs + h].contiguous()          # my last rows  -> `down`'s top ghosts
+        if self.world == 1:
+            ext[:, :, :h] = bot_rows
+            ext[:, :, h + Hs:] = top_rows
+            return
+        recv_top = torch.empty_like(top_rows)
+        recv_bot = torch.empty_like(bot_rows)
+        ops = [dist.P2POp(dist.isend, top_rows, self.up, self.group, tag=0),
+               dist.P2POp(dist.isend, bot_rows, self.down, self.group, tag=1),
+               dist.P2POp(dist.irecv, recv_top, self.up, self.group, tag=1),
+               dist.P2POp(dist.irecv, recv_bot, self.down, self.group, tag=0)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        ext[:, :, :h] = recv_top
+        ext[:, :, h + Hs:] = recv_bot
+
+    def rollout(self, u_local: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float,
+                steps: int, step_fn: Optional[Callable] = None) -> torch.Tensor:
+        """``steps`` forward-Euler steps on this rank's slab.  ``step_fn(ext, kernels, symnet, L,
+        dt, halo, out, out_row_offset)`` defaults to the CUDA slab step; it must write the new
+        interior rows into ``out`` starting at ``out_row_offset``."""
+        if step_fn is None:
+            from . import ops
+            step_fn = ops.slab_step
+        h = self.halo
+        a = self.extend(u_local)
+        b = torch.empty_like(a)
+        for _ in range(steps):
+            self.exchange(a)
+            step_fn(a, kernels, symnet, L, dt, h, b, h)   # new interior lands inside the other buffer
+            a, b = b, a
+        return a[:, :, h:h + self.Hs].contiguous()

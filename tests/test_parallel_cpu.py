@@ -1,0 +1,107 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: batch sharding + flat gradient
+all-reduce (DIST-2) and slab decomposition + ring halo exchange (DIST-1).  The per-rank compute is
+the CPU oracle here (the CUDA kernels need a GPU); what is under test is the exchange logic."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pdenet_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model(k=5, max_order=2, C=2, L=2, dx=0.3):
+    g = torch.Generator().manual_seed(3)
+    orders = O.order_list(max_order)
+    M = O.initial_moments(k, orders) + 1e-2 * torch.randn(len(orders), k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    sym = 0.1 * torch.randn(C, O.symnet_param_count(C * len(orders), L), generator=g, dtype=torch.float64)
+    u0 = torch.randn(4, C, 16, 12, generator=g, dtype=torch.float64)
+    return Ks, sym, u0
+
+
+def _oracle_slab_step(ext, Ks, sym, L, dt, halo, out, out_row_offset):
+    """Non-periodic-in-H step on an extended slab, built from the oracle's periodic step: pad H
+    periodically is wrong for a slab, so evaluate on the extended block and keep interior rows
+    (rows within `halo` of the block edge are contaminated by the wrap and discarded)."""
+    Hs = ext.shape[2] - 2 * halo
+    full = O.step(ext, Ks, sym, L, dt)
+    out[:, :, out_row_offset:out_row_offset + Hs] = full[:, :, halo:halo + Hs]
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pdenet_b200  # noqa: F401
+        from pdenet_b200 import parallel as PP
+        torch.set_num_threads(1)
+        Ks, sym, u0 = _model()
+        L, dt, steps = 2, 1e-2, 3
+        # ---- DIST-2: batch-sharded gradients, one flat all-reduce
+        b0, nb = PP.shard_range(u0.shape[0], rank, world)
+        Kc, sc = Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+        out = O.rollout(u0[b0:b0 + nb], Kc, sc, L, dt, steps)[-1]
+        loss = out.square().sum() / u0[0].numel() / u0.shape[0]
+        loss.backward()
+        total = PP.flat_allreduce([Kc.grad, sc.grad], extra=loss.detach())
+        # ---- DIST-1: slab decomposition with ring halo exchange
+        slab = PP.SlabDecomposition(u0.shape[2], 2, rank, world)
+        mine = u0[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
+        fin = slab.rollout(mine, Ks, sym, L, dt, steps, step_fn=_oracle_slab_step)
+        q.put((rank, Kc.grad, sc.grad, float(total), fin))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_dp_and_slab_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    Ks, sym, u0 = _model()
+    L, dt, steps = 2, 1e-2, 3
+    Kc, sc = Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    ref = O.rollout(u0, Kc, sc, L, dt, steps)[-1]
+    loss = ref.square().sum() / u0[0].numel() / u0.shape[0]
+    loss.backward()
+    for rank, gk, gs, tot, fin in res:
+        assert torch.allclose(gk, Kc.grad, rtol=1e-11, atol=1e-14)
+        assert torch.allclose(gs, sc.grad, rtol=1e-11, atol=1e-14)
+        assert abs(tot - float(loss)) < 1e-12 * max(1.0, abs(float(loss)))
+    full = torch.cat([r[4] for r in res], dim=2)
+    assert torch.allclose(full, ref, rtol=1e-12, atol=1e-13)
+
+
+def test_shard_range_and_single_rank_slab():
+    import pdenet_b200  # noqa: F401
+    from pdenet_b200 import parallel as PP
+    for total, world in [(256, 8), (10, 4), (3, 4)]:
+        got = [PP.shard_range(total, r, world) for r in range(world)]
+        assert sum(n for _, n in got) == total
+        assert all(got[i][0] + got[i][1] == got[i + 1][0] for i in range(world - 1))
+    # world == 1: ghosts wrap onto the rank's own rows -> identical to the periodic rollout
+    Ks, sym, u0 = _model()
+    slab = PP.SlabDecomposition(u0.shape[2], 2, 0, 1)
+    fin = slab.rollout(u0, Ks, sym, 2, 1e-2, 2, step_fn=_oracle_slab_step)
+    assert torch.allclose(fin, O.rollout(u0, Ks, sym, 2, 1e-2, 2)[-1], rtol=1e-12, atol=1e-13)

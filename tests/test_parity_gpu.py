@@ -328,6 +328,19 @@ def test_slab_step_equals_periodic_step(P, cuda_device, dtype):
     assert torch.equal(torch.cat(parts, dim=2), full)
 
 
+def test_slab_rollout_single_rank(P, cuda_device):
+    """SlabDecomposition.rollout with the CUDA slab step (world 1: ghosts wrap onto own rows)."""
+    from pdenet_b200 import parallel as PP
+    k, max_order, C, L, dx, dt = 5, 2, 2, 2, 0.1, 1e-3
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 43)
+    Ks = O.scaled_kernels(M, scales).to(cuda_device)
+    sym = sym.to(cuda_device)
+    u = smooth_field(2, C, 40, 36, 44).to(cuda_device)
+    ref = P.rollout(u, Ks, sym, L, dt, 3, last_only=True)
+    got = PP.SlabDecomposition(40, 2, 0, 1).rollout(u, Ks, sym, L, dt, 3)
+    assert torch.equal(got, ref)
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib
