@@ -161,7 +161,7 @@ def oracle_pass(sample, threads):
     return B * H * W * blocks / dt, dt
 
 
-CPU_SAMPLE = dict(B=4, H=1024, W=1024, blocks=2)
+CPU_SAMPLE = dict(B=8, H=1024, W=1024, blocks=2)
 
 
 def cpu_baseline(threads):

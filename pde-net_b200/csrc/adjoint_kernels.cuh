@@ -217,7 +217,7 @@ template <typename T, int K> struct FGradCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int VEC = VecOf<T>::N;
   static constexpr int RW = 8;
-  static constexpr int MT = 4; // micro-tiles (of RW rows) per lane per tile (2 CTAs/SM fit in shared memory)
+  static constexpr int MT = 8; // micro-tiles (of RW rows) per lane per tile
   static constexpr int TW = 32 * VEC, TH = RW * MT;
   static constexpr int NV = (VEC + K - 1 + VEC - 1) / VEC;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
@@ -227,7 +227,8 @@ template <typename T, int K> struct FGradCfg {
   static constexpr int VLB = KK <= 16 ? 16 : (KK <= 32 ? 32 : 64);
   static constexpr int TILE_ELEMS = SR * PITCH;
   static constexpr int NT = 192; // 6 warps, 2 CTAs per SM
-  static constexpr int GST_ELEMS = 2 * RW * 32 * VEC; // per-warp double-buffered g micro-tile
+  static constexpr int GST_ELEMS = RW * 32 * VEC; // per-warp g micro-tile staging (single buffer: it is
+                                                  // drained into registers before the next copy is issued)
   static __host__ size_t smem_bytes() { return (size_t)(2 * TILE_ELEMS + (NT / 32) * GST_ELEMS) * sizeof(T); }
 };
 
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
   T *ubuf = reinterpret_cast<T *>(smem_raw); // [2][SR][PITCH]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  T *gst = ubuf + 2 * TILE + warp * Cfg::GST_ELEMS + lane * VEC; // [2][RW][32 lanes][VEC], this lane's slots
+  T *gst = ubuf + 2 * TILE + warp * Cfg::GST_ELEMS + lane * VEC; // [RW][32 lanes][VEC], this lane's slots
   const int H = p.H, W = p.W, N = p.N, C = p.C;
   const int parts = (NTHREADS / 32) / p.nw, part = warp / p.nw;
   const int n = p.n0 + warp % p.nw;
@@ -285,13 +286,13 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
 
       // g micro-tile: global -> this warp's staging slots (cp.async, zero-filled outside the
       // domain), one micro-tile ahead of the compute
-      auto stage_g = [&](int mt, int gb) {
+      auto stage_g = [&](int mt) {
 #pragma unroll
         for (int j = 0; j < RW; ++j) {
           const int y = ty * TH + mt * RW + j;
           const bool ok = (y < H) && (x0 < W);
           const T *grow = gimg + (size_t)((ok ? y : 0) + p.g_off) * W + (ok ? x0 : 0);
-          T *dst = gst + (gb * RW + j) * 32 * VEC;
+          T *dst = gst + j * 32 * VEC;
           if (p.vec_ok) {
             cp_async_16_zfill(dst, grow, ok);
           } else {
@@ -301,10 +302,9 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
         }
       };
 
-      // group order per item: G(first), U(next item), G(second), G(third), ...  so the next
-      // item's u tile never sits in front of the g micro-tile the warp is about to consume
-      int gb = 0;
-      stage_g(part, 0);
+      // cp.async group order per item: G(first), U(next item), then G(mt+1) right after G(mt) has
+      // been drained into registers -- the staging slots are single-buffered and lane-private.
+      stage_g(part);
       cp_async_commit();
       if (item + (int)gridDim.x < p.n_items) stage_u(item + gridDim.x, ub ^ 1);
       cp_async_commit();
@@ -312,16 +312,16 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
 #pragma unroll 1
       for (int mt = part; mt < MT; mt += parts) {
         if (ty * TH + mt * RW >= H) break; // warp-uniform: nothing left in this tile
-        if (mt + parts < MT) stage_g(mt + parts, gb ^ 1);
-        cp_async_commit();
         if (first)
-          cp_async_wait<2>();
+          cp_async_wait<1>(); // G(first) landed; U(next) may still be in flight
         else
-          cp_async_wait<1>();
+          cp_async_wait<0>();
         first = false;
         T gc[RW][VEC];
 #pragma unroll
-        for (int j = 0; j < RW; ++j) ld_vec(gst + (gb * RW + j) * 32 * VEC, &gc[j][0]);
+        for (int j = 0; j < RW; ++j) ld_vec(gst + j * 32 * VEC, &gc[j][0]);
+        if (mt + parts < MT) stage_g(mt + parts);
+        cp_async_commit();
         const T *um = us + mt * RW * PITCH;
 #pragma unroll
         for (int rho = 0; rho < RW + K - 1; ++rho) {
@@ -339,7 +339,6 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
             }
           }
         }
-        gb ^= 1;
       }
     }
     __syncthreads(); // the u tile in `ub` is free again

@@ -12,7 +12,7 @@ template <typename KernelT> static int allow_smem(KernelT kern, size_t smem) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 0 : -4;
 }
 
-template <typename T, int K, int N, int C, int MODE, int VL>
+template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1>
 static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
   using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
   StepParams<T> p = p_in;
@@ -21,7 +21,7 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.n_items = p.B * p.tiles_x * p.tiles_y;
   const int grid = p.n_items < sms ? p.n_items : sms;
   const size_t smem = Cfg::smem_bytes(p.Psym, MODE == MODE_BWD_A);
-  auto kern = step_kernel<T, K, N, C, MODE, VL>;
+  auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
@@ -31,9 +31,14 @@ template <typename T, int K>
 int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st) {
 #define PDENET_CASE(NN, CC)                                                                                       \
   if (N == NN && C == CC) {                                                                                      \
-    if (mode == MODE_FWD) return launch_step_one<T, K, NN, CC, MODE_FWD, 16>(p, sms, st);                       \
+    if (mode == MODE_FWD) {                                                                                      \
+      if (p.L == 2) return launch_step_one<T, K, NN, CC, MODE_FWD, 16, 2>(p, sms, st);                           \
+      return launch_step_one<T, K, NN, CC, MODE_FWD, 16>(p, sms, st);                                            \
+    }                                                                                                            \
     if (mode == MODE_FEATS) return launch_step_one<T, K, NN, CC, MODE_FEATS, 16>(p, sms, st);                   \
     if (mode == MODE_BWD_A) {                                                                                    \
+      if constexpr (NN * CC + 3 <= 16)                                                                           \
+        if (VL == 16 && p.L == 2) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16, 2>(p, sms, st);           \
       if constexpr (NN * CC + 1 < 16)                                                                            \
         if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, sms, st);                         \
       if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, sms, st);                           \

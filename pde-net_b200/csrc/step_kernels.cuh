@@ -75,11 +75,14 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
 // SymNet forward for PP points (row a7).  d: derivative features in registers, prm: this output
 // channel's flat parameters in shared memory (broadcast reads).  Layers are looped at run time;
 // the few per-layer scalars (p, q, product units) live in small local arrays.
-template <typename T, int M, int P, int PP, int J0, bool KEEP>
-__device__ __forceinline__ int symnet_forward(const T (&d)[M][P], const T *prm, int L, T (&out)[PP],
+// LT >= 0: the depth is a compile-time constant (layer loops fully unrolled, parameter offsets become
+// immediates, the per-layer scalars stay in registers); LT < 0: run-time depth L_rt.
+template <typename T, int M, int P, int PP, int J0, bool KEEP, int LT, bool NEED_OUT = true>
+__device__ __forceinline__ int symnet_forward(const T (&d)[M][P], const T *prm, int L_rt, T (&out)[PP],
                                               T (*un)[PP], T (*pl)[PP], T (*ql)[PP]) {
+  const int L = LT >= 0 ? LT : L_rt;
   int off = 0;
-#pragma unroll 1
+#pragma unroll(LT >= 0 ? 8 : 1)
   for (int i = 0; i < L; ++i) {
     const int mi = M + i;
     T pv[PP], qv[PP];
@@ -97,7 +100,7 @@ __device__ __forceinline__ int symnet_forward(const T (&d)[M][P], const T *prm, 
         qv[jj] = fma_(w1, d[f][J0 + jj], qv[jj]);
       }
     }
-#pragma unroll 1
+#pragma unroll(LT >= 0 ? 8 : 1)
     for (int i2 = 0; i2 < i; ++i2) {
       const T w0 = prm[off + M + i2], w1 = prm[off + mi + M + i2];
 #pragma unroll
@@ -116,19 +119,21 @@ __device__ __forceinline__ int symnet_forward(const T (&d)[M][P], const T *prm, 
     }
     off += 2 * mi + 2;
   }
+  if (NEED_OUT) {
 #pragma unroll
-  for (int jj = 0; jj < PP; ++jj) out[jj] = prm[off + M + L];
+    for (int jj = 0; jj < PP; ++jj) out[jj] = prm[off + M + L];
 #pragma unroll
-  for (int f = 0; f < M; ++f) {
-    const T wf = prm[off + f];
+    for (int f = 0; f < M; ++f) {
+      const T wf = prm[off + f];
 #pragma unroll
-    for (int jj = 0; jj < PP; ++jj) out[jj] = fma_(wf, d[f][J0 + jj], out[jj]);
-  }
-#pragma unroll 1
-  for (int i2 = 0; i2 < L; ++i2) {
-    const T wf = prm[off + M + i2];
+      for (int jj = 0; jj < PP; ++jj) out[jj] = fma_(wf, d[f][J0 + jj], out[jj]);
+    }
+#pragma unroll(LT >= 0 ? 8 : 1)
+    for (int i2 = 0; i2 < L; ++i2) {
+      const T wf = prm[off + M + i2];
 #pragma unroll
-    for (int jj = 0; jj < PP; ++jj) out[jj] = fma_(wf, un[i2][jj], out[jj]);
+      for (int jj = 0; jj < PP; ++jj) out[jj] = fma_(wf, un[i2][jj], out[jj]);
+    }
   }
   return off; // offset of the final layer's weights
 }
@@ -161,9 +166,10 @@ template <typename T, int NE> __device__ __forceinline__ T transpose_sum(const T
 // features) over output channels and reduces the parameter gradients (rows a7/a11).
 // VL (16 or 32) >= M + L + 1 is the padded length of one parameter-gradient vector
 // [features 0..M), product units [M..M+L), bias at VL-1].
-template <typename T, int M, int P, int PP, int J0, int VL, int C>
-__device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms, int Psym, int L,
+template <typename T, int M, int P, int PP, int J0, int VL, int C, int LT>
+__device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms, int Psym, int L_rt,
                                                const T (&lamv)[C][PP], T (&gacc)[M][PP], double *sg, T *scratch) {
+  const int L = LT >= 0 ? LT : L_rt;
   constexpr int UCAP = (VL - 1 - M) < kMaxLayers ? (VL - 1 - M) : kMaxLayers; // static bound on L
   constexpr int TP = TransposeCfg<T>::PITCH;
   const int lane = threadIdx.x & 31;
@@ -178,7 +184,7 @@ __device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms
     double *sgc = sg + co * Psym;
     T un[kMaxLayers][PP], pl[kMaxLayers][PP], ql[kMaxLayers][PP], eta[kMaxLayers][PP];
     T fout[PP];
-    int off = symnet_forward<T, M, P, PP, J0, true>(d, prm, L, fout, un, pl, ql);
+    int off = symnet_forward<T, M, P, PP, J0, true, LT, false>(d, prm, L, fout, un, pl, ql);
     // ---- final linear layer: out = wf . h + bf, seed = dt * lambda
     {
       T *col = scratch + lane;
@@ -219,7 +225,7 @@ __device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms
         sgc[off + M + L] += (double)tot;
     }
     // ---- hidden product layers, last to first
-#pragma unroll 1
+#pragma unroll(LT >= 0 ? 8 : 1)
     for (int i = L - 1; i >= 0; --i) {
       const int mi = M + i;
       off -= 2 * mi + 2;
@@ -286,7 +292,7 @@ __device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms
 }
 
 // One half-strip (2 points) of kernel A's epilogue: seed, SymNet reverse, store g.
-template <typename T, int M, int P, int J0, int VL, int C>
+template <typename T, int M, int P, int J0, int VL, int C, int LT>
 __device__ __forceinline__ void reverse_half(const T (&d)[M][P], const T *syms, int Psym, int L,
                                              const bool (&valid)[P], const T (&lam_raw)[C][P],
                                              const StepParams<T> &p, int b, int y0, int x, double *sg,
@@ -299,17 +305,21 @@ __device__ __forceinline__ void reverse_half(const T (&d)[M][P], const T *syms, 
 #pragma unroll
     for (int jj = 0; jj < PP; ++jj) lamv[co][jj] = p.dt * lam_raw[co][J0 + jj];
   T gacc[M][PP];
-  symnet_reverse<T, M, P, PP, J0, VL, C>(d, syms, Psym, L, lamv, gacc, sg, scratch);
+  symnet_reverse<T, M, P, PP, J0, VL, C, LT>(d, syms, Psym, L, lamv, gacc, sg, scratch);
+  // running pointer over the feature planes: one 64-bit add per plane instead of a full index
+  T *gp = p.g + ((size_t)b * M * p.g_rows + (y0 + J0 + p.g_off)) * W + x;
+  const size_t plane = (size_t)p.g_rows * W;
 #pragma unroll
-  for (int f = 0; f < M; ++f)
+  for (int f = 0; f < M; ++f) {
 #pragma unroll
     for (int jj = 0; jj < PP; ++jj)
-      if (valid[J0 + jj])
-        p.g[((size_t)(b * M + f) * p.g_rows + (y0 + J0 + jj + p.g_off)) * W + x] = gacc[f][jj];
+      if (valid[J0 + jj]) gp[(size_t)jj * W] = gacc[f][jj];
+    gp += plane;
+  }
 }
 
 // --------------------------------------------------------------------------------------------
-template <typename T, int K, int N, int C, int MODE, int VL>
+template <typename T, int K, int N, int C, int MODE, int VL, int LT>
 __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const StepParams<T> p) {
   using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
@@ -383,11 +393,11 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
       T lam_raw[WITH_GRAD ? C : 1][P];
       if constexpr (WITH_GRAD) {
 #pragma unroll
-        for (int co = 0; co < C; ++co)
+        for (int co = 0; co < C; ++co) {
+          const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
 #pragma unroll
-          for (int j = 0; j < P; ++j)
-            lam_raw[co][j] =
-                valid[j] ? p.lam[((size_t)(b * C + co) * p.lam_rows + (y0 + j + p.lam_off)) * W + x] : T(0);
+          for (int j = 0; j < P; ++j) lam_raw[co][j] = valid[j] ? lp[(size_t)j * W] : T(0);
+        }
       }
       // ---- derivative features of every channel at the strip's P points (rows a5-a6)
       T d[M][P];
@@ -435,18 +445,17 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 #pragma unroll 1
         for (int co = 0; co < C; ++co) {
           T un[kMaxLayers][P], fout[P];
-          symnet_forward<T, M, P, P, 0, false>(d, syms + co * Psym, L, fout, un, un, un);
+          symnet_forward<T, M, P, P, 0, false, LT>(d, syms + co * Psym, L, fout, un, un, un);
           const T *uc = tile + (co * SR + row0 + R) * PITCH + col + R;
+          T *op = p.out + ((size_t)(b * C + co) * p.out_rows + (y0 + p.out_off)) * W + x;
 #pragma unroll
           for (int j = 0; j < P; ++j)
-            if (valid[j])
-              p.out[((size_t)(b * C + co) * p.out_rows + (y0 + j + p.out_off)) * W + x] =
-                  fma_(p.dt, fout[j], uc[j * PITCH]);
+            if (valid[j]) op[(size_t)j * W] = fma_(p.dt, fout[j], uc[j * PITCH]);
         }
       } else if constexpr (MODE == MODE_BWD_A) {
         // ---- SymNet reverse, two points at a time (register budget), rows a7/a11
-        reverse_half<T, M, P, 0, VL, C>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
-        reverse_half<T, M, P, 2, VL, C>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        reverse_half<T, M, P, 0, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
       } else if constexpr (MODE == MODE_LIN_FWD) {
         // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1
         const T *coe = p.symnet;
