@@ -89,10 +89,10 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
     b = t / C;
   };
   const int xs = p.vec_ok ? Cfg::XS : 0; // periodic in x: a shifted tiling covers the same points
-  auto stage_g = [&](int item, int n, int gb) {
-    int b, c, ty, tx;
-    decode(item, b, c, ty, tx);
-    const T *img = p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W;
+  const size_t plane = (size_t)p.g_rows * W;
+  // stage filter n of the item whose first g plane is `img0` and whose tile is (ty, tx)
+  auto stage_g = [&](const T *img0, int ty, int tx, int n, int gb) {
+    const T *img = img0 + (size_t)n * plane;
     if (p.vec_ok)
       stage_tile_async_vec<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
                                                  tx * TW - xs - R, H, W);
@@ -102,15 +102,19 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
   };
 
   int item = blockIdx.x, gb = 0;
-  if (item < p.n_items) stage_g(item, 0, 0);
+  int b = 0, c = 0, ty = 0, tx = 0;     // current item
+  int nb_ = 0, nc_ = 0, nty = 0, ntx = 0; // next item (decoded once, when its first tile is prefetched)
+  if (item < p.n_items) {
+    decode(item, b, c, ty, tx);
+    stage_g(p.g + (size_t)(b * C + c) * N * plane, ty, tx, 0, 0);
+  }
   cp_async_commit();
 
   const int lrow = warp * RW, lcol = lane * VEC;
 
   for (; item < p.n_items; item += gridDim.x) {
-    int b, c, ty, tx;
-    decode(item, b, c, ty, tx);
     const int y0 = ty * TH + lrow, x0 = tx * TW - xs + lcol; // x0 in [-xs, W - xs)
+    const T *img0 = p.g + (size_t)(b * C + c) * N * plane;
 
     T lacc[RW][VEC];
 #pragma unroll
@@ -122,9 +126,10 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
     for (int n = 0; n < N; ++n) {
       // ---- prefetch the next stage (next filter of this item, or the first of the next item)
       if (n + 1 < N) {
-        stage_g(item, n + 1, gb ^ 1);
+        stage_g(img0, ty, tx, n + 1, gb ^ 1);
       } else if (item + (int)gridDim.x < p.n_items) {
-        stage_g(item + gridDim.x, 0, gb ^ 1);
+        decode(item + gridDim.x, nb_, nc_, nty, ntx);
+        stage_g(p.g + (size_t)(nb_ * C + nc_) * N * plane, nty, ntx, 0, gb ^ 1);
       }
       cp_async_commit();
       cp_async_wait<1>();
@@ -166,34 +171,45 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
     // whole row group before any use (clamped addresses instead of branches) so they overlap.
     {
       const size_t img = (size_t)(b * C + c);
+      const T *li = p.lam_in ? p.lam_in + (img * p.li_rows + p.li_off) * W : nullptr;
+      const T *inj = p.inject ? p.inject + (img * p.inj_rows + p.inj_off) * W : nullptr;
+      T *lo = p.lam_out + (img * p.lo_rows + p.lo_off) * W;
+      int xx[VEC];
+      bool okx[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int xg = x0 + i;
+        okx[i] = xg < W - xs;
+        xx[i] = okx[i] ? (xg < 0 ? xg + W : xg) : 0;
+      }
 #pragma unroll
       for (int j0 = 0; j0 < RW; j0 += 4) {
         T add[4][VEC];
-        bool ok[4][VEC];
-        int xx[4][VEC];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int y = y0 + j0 + jj;
+          const size_t ro = (size_t)(y < H ? y : 0) * W;
 #pragma unroll
           for (int i = 0; i < VEC; ++i) {
-            const int xg = x0 + i;
-            ok[jj][i] = (y < H) && (xg < W - xs);
-            xx[jj][i] = xg < 0 ? xg + W : xg;
-            const int ys = ok[jj][i] ? y : 0, xc = ok[jj][i] ? xx[jj][i] : 0;
             T v = T(0);
-            if (p.lam_in) v = p.lam_in[(img * p.li_rows + (ys + p.li_off)) * W + xc];
-            if (p.inject) v += p.inject[(img * p.inj_rows + (ys + p.inj_off)) * W + xc];
+            if (li) v = li[ro + xx[i]];
+            if (inj) v += inj[ro + xx[i]];
             add[jj][i] = v;
           }
         }
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
+        for (int jj = 0; jj < 4; ++jj) {
+          const int y = y0 + j0 + jj;
 #pragma unroll
           for (int i = 0; i < VEC; ++i)
-            if (ok[jj][i])
-              p.lam_out[(img * p.lo_rows + (y0 + j0 + jj + p.lo_off)) * W + xx[jj][i]] = lacc[j0 + jj][i] + add[jj][i];
+            if (y < H && okx[i]) lo[(size_t)y * W + xx[i]] = lacc[j0 + jj][i] + add[jj][i];
+        }
       }
     }
+    b = nb_;
+    c = nc_;
+    ty = nty;
+    tx = ntx;
   }
   cp_async_wait<0>();
 }
@@ -286,18 +302,21 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
 
       // g micro-tile: global -> this warp's staging slots (cp.async, zero-filled outside the
       // domain), one micro-tile ahead of the compute
+      const bool okx = x0 < W;
+      const T *gcol = gimg + (size_t)p.g_off * W + (okx ? x0 : 0);
       auto stage_g = [&](int mt) {
+        const int ybase = ty * TH + mt * RW;
+        const T *grow = gcol + (size_t)ybase * W;
 #pragma unroll
         for (int j = 0; j < RW; ++j) {
-          const int y = ty * TH + mt * RW + j;
-          const bool ok = (y < H) && (x0 < W);
-          const T *grow = gimg + (size_t)((ok ? y : 0) + p.g_off) * W + (ok ? x0 : 0);
+          const bool ok = okx && (ybase + j < H);
+          const T *src = ok ? grow + (size_t)j * W : gcol;
           T *dst = gst + j * 32 * VEC;
           if (p.vec_ok) {
-            cp_async_16_zfill(dst, grow, ok);
+            cp_async_16_zfill(dst, src, ok);
           } else {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) dst[i] = (ok && x0 + i < W) ? grow[i] : T(0);
+            for (int i = 0; i < VEC; ++i) dst[i] = (ok && x0 + i < W) ? src[i] : T(0);
           }
         }
       };

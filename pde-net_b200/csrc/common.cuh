@@ -76,12 +76,17 @@ __device__ __forceinline__ void stage_tile_async(T *dst, const T *__restrict__ i
   int gx[NCB];
 #pragma unroll
   for (int j = 0; j < NCB; ++j) gx[j] = wrap_index(x0 + lane + 32 * j, W);
+  int gyw = y0 + warp; // logical row, wrapped incrementally (one mod per call, not per row)
+  if (wrap_y) gyw = wrap_index(gyw, H);
   for (int row = warp; row < ROWS; row += NT / 32) {
-    int gy = y0 + row;
-    if (wrap_y) gy = wrap_index(gy, H);
-    gy += row_off;
+    int gy = gyw + row_off;
     // slab mode: rows outside the buffer can only belong to masked (out-of-domain) outputs
     gy = gy < 0 ? 0 : (gy >= rows_buf ? rows_buf - 1 : gy);
+    gyw += NT / 32;
+    if (wrap_y && gyw >= H) {
+      gyw -= H;
+      if (gyw >= H) gyw %= H;
+    }
     const T *srow = img + (size_t)gy * W;
     T *drow = dst + row * PITCH;
 #pragma unroll
@@ -105,11 +110,16 @@ __device__ __forceinline__ void stage_tile_async_vec(T *dst, const T *__restrict
   int gx[NCB];
 #pragma unroll
   for (int j = 0; j < NCB; ++j) gx[j] = wrap_index(x0 + (lane + 32 * j) * VEC, W);
+  int gyw = y0 + warp;
+  if (wrap_y) gyw = wrap_index(gyw, H);
   for (int row = warp; row < ROWS; row += NT / 32) {
-    int gy = y0 + row;
-    if (wrap_y) gy = wrap_index(gy, H);
-    gy += row_off;
+    int gy = gyw + row_off;
     gy = gy < 0 ? 0 : (gy >= rows_buf ? rows_buf - 1 : gy);
+    gyw += NT / 32;
+    if (wrap_y && gyw >= H) {
+      gyw -= H;
+      if (gyw >= H) gyw %= H;
+    }
     const T *srow = img + (size_t)gy * W;
     T *drow = dst + row * PITCH;
 #pragma unroll

@@ -67,7 +67,7 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static __host__ __device__ constexpr int grad_elems(int Psym) { return round_up(C * Psym, 2); }
   static __host__ size_t smem_bytes(int Psym, bool with_grad) {
     size_t e = W_ELEMS + sym_elems(Psym) + 2 * TILE_ELEMS + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
-    return e * sizeof(T) + (with_grad ? (size_t)(NT / 32) * grad_elems(Psym) * sizeof(double) : 0);
+    return e * sizeof(T) + (with_grad ? (size_t)(NT / 32) * grad_elems(Psym) * sizeof(double) + 64 * sizeof(int) : 0);
   }
 };
 
@@ -291,6 +291,218 @@ __device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Static-depth fast path of the SymNet reverse: all P points of the strip at once, in two sweeps.
+//   sweep 1 (per output channel): forward (p_i, q_i, units) and the 2*LT+1 error signals
+//            S = (dt*lambda, pbar_i, qbar_i); the few unit-weight / bias gradients go to one
+//            "tail" transpose;
+//   sweep 2 (per derivative feature f): g_f = sum_{co,s} S * W[co,s,f] is stored straight away and
+//            the C*(2LT+1) parameter-gradient partials sum_j S*d_f fill FG features' worth of rows
+//            of the transpose scratch before each cross-lane row sum.
+// Compared with the half-strip path this halves the transposes and parameter loads per point and
+// never holds the g accumulators in registers.
+template <int M, int C, int LT> struct RevFullCfg {
+  static constexpr int NS = 2 * LT + 1;               // error signals per output channel
+  static constexpr int RPF = C * NS;                  // scratch rows per feature
+  static constexpr int FG = 32 / (RPF > 0 ? RPF : 1); // features per transpose
+  static constexpr int NTAIL = C * (LT + 1) * (LT + 1);
+  static constexpr bool OK = LT >= 0 && RPF <= 32 && NTAIL <= 32 && FG >= 1;
+};
+
+// Tables (shared memory, built once per kernel): feat_base[l] = parameter index (within the
+// [C][Psym] block) that scratch row l of a feature transpose maps to for feature 0 of the group
+// (add the group's first feature); tail_idx[l] = parameter index of tail row l.
+template <int M, int C, int LT> __device__ void build_rev_tables(int Psym, int *feat_base, int *tail_idx) {
+  using RC = RevFullCfg<M, C, LT>;
+  int offs[LT + 1];
+  int off = 0;
+  for (int i = 0; i < LT; ++i) {
+    offs[i] = off;
+    off += 2 * (M + i) + 2;
+  }
+  offs[LT] = off;
+  for (int l = 0; l < 32; ++l) {
+    int v = -1;
+    if (l < RC::FG * RC::RPF) {
+      const int fl = l / RC::RPF, rem = l % RC::RPF, co = rem / RC::NS, sidx = rem % RC::NS;
+      if (sidx == 0) {
+        v = co * Psym + offs[LT] + fl;
+      } else {
+        const int i = (sidx - 1) / 2, r = (sidx - 1) % 2;
+        v = co * Psym + offs[i] + r * (M + i) + fl;
+      }
+    }
+    feat_base[l] = v;
+    tail_idx[l] = -1;
+  }
+  int t = 0;
+  for (int co = 0; co < C; ++co) {
+    for (int i2 = 0; i2 < LT; ++i2) tail_idx[t++] = co * Psym + offs[LT] + M + i2;
+    tail_idx[t++] = co * Psym + offs[LT] + M + LT;
+    for (int i = LT - 1; i >= 0; --i)
+      for (int r = 0; r < 2; ++r) {
+        for (int i2 = 0; i2 < i; ++i2) tail_idx[t++] = co * Psym + offs[i] + r * (M + i) + M + i2;
+        tail_idx[t++] = co * Psym + offs[i] + 2 * (M + i) + r;
+      }
+  }
+}
+
+template <typename T, int M, int P, int C, int LT>
+__device__ __forceinline__ void symnet_reverse_full(const T (&d)[M][P], const T *syms, int Psym,
+                                                    const T (&lam)[C][P], const bool (&valid)[P], T *gp,
+                                                    size_t plane, int W, double *sg, T *scratch,
+                                                    const int *feat_base, const int *tail_idx) {
+  using RC = RevFullCfg<M, C, LT>;
+  constexpr int NS = RC::NS, RPF = RC::RPF, FG = RC::FG, NTAIL = RC::NTAIL;
+  constexpr int TP = TransposeCfg<T>::PITCH;
+  constexpr int LA = LT > 0 ? LT : 1;
+  const int lane = threadIdx.x & 31;
+  T *col = scratch + lane;
+  T S[C][NS][P];
+  int t = 0; // tail row (compile-time after unrolling; same enumeration as build_rev_tables)
+#pragma unroll
+  for (int co = 0; co < C; ++co) {
+    const T *prm = syms + co * Psym;
+    T pl[LA][P], ql[LA][P], un[LA][P], eta[LA][P];
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < LT; ++i) {
+      const int mi = M + i;
+      T pv[P], qv[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        pv[j] = prm[off + 2 * mi];
+        qv[j] = prm[off + 2 * mi + 1];
+      }
+#pragma unroll
+      for (int f = 0; f < M; ++f) {
+        const T w0 = prm[off + f], w1 = prm[off + mi + f];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          pv[j] = fma_(w0, d[f][j], pv[j]);
+          qv[j] = fma_(w1, d[f][j], qv[j]);
+        }
+      }
+#pragma unroll
+      for (int i2 = 0; i2 < i; ++i2) {
+        const T w0 = prm[off + M + i2], w1 = prm[off + mi + M + i2];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          pv[j] = fma_(w0, un[i2][j], pv[j]);
+          qv[j] = fma_(w1, un[i2][j], qv[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        pl[i][j] = pv[j];
+        ql[i][j] = qv[j];
+        un[i][j] = pv[j] * qv[j];
+      }
+      off += 2 * mi + 2;
+    }
+    // final layer: signal 0 = dt*lambda; unit weights and bias of w_f go to the tail
+#pragma unroll
+    for (int j = 0; j < P; ++j) S[co][0][j] = lam[co][j];
+#pragma unroll
+    for (int i2 = 0; i2 < LT; ++i2) {
+      const T wf = prm[off + M + i2];
+      T v = T(0);
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        eta[i2][j] = lam[co][j] * wf;
+        v = fma_(lam[co][j], un[i2][j], v);
+      }
+      col[(t++) * TP] = v;
+    }
+    {
+      T v = T(0);
+#pragma unroll
+      for (int j = 0; j < P; ++j) v += lam[co][j];
+      col[(t++) * TP] = v;
+    }
+#pragma unroll
+    for (int i = LT - 1; i >= 0; --i) {
+      const int mi = M + i;
+      off -= 2 * mi + 2;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        S[co][1 + 2 * i][j] = eta[i][j] * ql[i][j];
+        S[co][2 + 2 * i][j] = eta[i][j] * pl[i][j];
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int i2 = 0; i2 < i; ++i2) {
+          const T w = prm[off + r * mi + M + i2];
+          T v = T(0);
+#pragma unroll
+          for (int j = 0; j < P; ++j) {
+            eta[i2][j] = fma_(S[co][1 + 2 * i + r][j], w, eta[i2][j]);
+            v = fma_(S[co][1 + 2 * i + r][j], un[i2][j], v);
+          }
+          col[(t++) * TP] = v;
+        }
+        T v = T(0);
+#pragma unroll
+        for (int j = 0; j < P; ++j) v += S[co][1 + 2 * i + r][j];
+        col[(t++) * TP] = v;
+      }
+    }
+  }
+  {
+    const T tot = transpose_sum<T, 32>(scratch);
+    if (lane < NTAIL) sg[tail_idx[lane]] += (double)tot;
+  }
+  // ---- sweep 2: derivative features
+  int offs[LA + 1];
+  {
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < LT; ++i) {
+      offs[i] = off;
+      off += 2 * (M + i) + 2;
+    }
+    offs[LT > 0 ? LT : 0] = off;
+  }
+  const int fb = feat_base[lane];
+#pragma unroll
+  for (int f0 = 0; f0 < M; f0 += FG) {
+#pragma unroll
+    for (int fl = 0; fl < FG; ++fl) {
+      const int f = f0 + fl;
+      if (f < M) {
+        T gv[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) gv[j] = T(0);
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+          const T *prm = syms + co * Psym;
+#pragma unroll
+          for (int sidx = 0; sidx < NS; ++sidx) {
+            const int woff = sidx == 0 ? offs[LT > 0 ? LT : 0]
+                                       : offs[(sidx - 1) / 2] + ((sidx - 1) % 2) * (M + (sidx - 1) / 2);
+            const T w = prm[woff + f];
+            T v = T(0);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+              gv[j] = fma_(S[co][sidx][j], w, gv[j]);
+              v = fma_(S[co][sidx][j], d[f][j], v);
+            }
+            col[(fl * RPF + co * NS + sidx) * TP] = v;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          if (valid[j]) gp[(size_t)j * W] = gv[j];
+        gp += plane;
+      }
+    }
+    const T tot = transpose_sum<T, 32>(scratch);
+    const int rows = (M - f0 < FG ? M - f0 : FG) * RPF;
+    if (lane < rows) sg[fb + f0] += (double)tot;
+  }
+}
+
 // One half-strip (2 points) of kernel A's epilogue: seed, SymNet reverse, store g.
 template <typename T, int M, int P, int J0, int VL, int C, int LT>
 __device__ __forceinline__ void reverse_half(const T (&d)[M][P], const T *syms, int Psym, int L,
@@ -369,6 +581,11 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   const int wx = warp & 1, wy = warp >> 1;
   double *sg = sgrad + warp * Cfg::grad_elems(Psym);
   T *scratch = tiles + 2 * Cfg::TILE_ELEMS + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (MODE_BWD_A)
+  int *rev_tables = reinterpret_cast<int *>(tiles + 2 * Cfg::TILE_ELEMS + (NT / 32) * TransposeCfg<T>::ELEMS);
+  constexpr bool REV_FULL = WITH_GRAD && RevFullCfg<M, C, LT>::OK;
+  if constexpr (REV_FULL) {
+    if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
+  }
 
   for (; item < p.n_items; item += gridDim.x) {
     const int next = item + gridDim.x;
@@ -454,8 +671,19 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
         }
       } else if constexpr (MODE == MODE_BWD_A) {
         // ---- SymNet reverse, two points at a time (register budget), rows a7/a11
-        reverse_half<T, M, P, 0, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
-        reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        if constexpr (REV_FULL) {
+          T lamv[C][P];
+#pragma unroll
+          for (int co = 0; co < C; ++co)
+#pragma unroll
+            for (int j = 0; j < P; ++j) lamv[co][j] = p.dt * lam_raw[co][j];
+          T *gp = p.g + ((size_t)b * M * p.g_rows + (y0 + p.g_off)) * W + x;
+          symnet_reverse_full<T, M, P, C, (LT >= 0 ? LT : 0)>(d, syms, Psym, lamv, valid, gp, (size_t)p.g_rows * W, W,
+                                                             sg, scratch, rev_tables, rev_tables + 32);
+        } else {
+          reverse_half<T, M, P, 0, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+          reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        }
       } else if constexpr (MODE == MODE_LIN_FWD) {
         // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1
         const T *coe = p.symnet;
