@@ -163,6 +163,10 @@ PDENET_API int pdenet_profile_read(double *ms_by_kind, long long *launches_by_ki
 /* ---- measurement helper: register-only FMA loop, returns elapsed ms for `flops` flops -------
  * (used by bench.py for the CUDA-core FLOP roofline denominator). */
 PDENET_API int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream);
+/* Register-operand probes of the FMA pipe: variant 0 = x = fma(x, a, b) with
+ * loop-invariant a, b (what pdenet_fma_peak runs); 1 = three distinct register operands per FMA,
+ * none shared with the neighbouring FMAs; 2 = one operand shared by 4 consecutive FMAs. */
+PDENET_API int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream);
 
 #ifdef __cplusplus
 }

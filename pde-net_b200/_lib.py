@@ -39,6 +39,7 @@ _PROTOS = {
     "pdenet_profile_enable": (_i, [_i]),
     "pdenet_profile_read": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "pdenet_fma_peak": (_i, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float), _vp]),
+    "pdenet_fma_probe": (_i, [_i, _i, _i, C.POINTER(_d), C.POINTER(C.c_float), _vp]),
 }
 
 

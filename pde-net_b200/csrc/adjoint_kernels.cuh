@@ -15,25 +15,9 @@
 //       cross-lane reduction happens once per launch instead of once per (tile, filter).
 #pragma once
 #include "common.cuh"
+#include "params.cuh"
 
 namespace pdenet {
-
-template <typename T> struct AdjParams {
-  const T *g; // [B][C*N][g_rows][W]
-  int g_rows, g_off;
-  int wrap_y;
-  const T *lam_in; // [B][C][li_rows][W]; NULL = 0
-  int li_rows, li_off;
-  const T *inject; // [B][C][inj_rows][W]; NULL = none
-  int inj_rows, inj_off;
-  T *lam_out; // [B][C][lo_rows][W]; NULL = skip the data gradient
-  int lo_rows, lo_off;
-  const T *kernels;   // [N][K][K]
-  const T *kernels0;  // if non-NULL: filter 0 is kernels0 [K][K] and `kernels` holds filters 1..N-1 (linear model)
-  int vec_ok;         // 1: g may be staged in 16-byte units (W % VEC == 0, base 16-byte aligned)
-  int B, C, N, H, W;
-  int tiles_x, tiles_y, n_items;
-};
 
 template <typename T, int K> struct AdjCfg {
   static constexpr int R = (K - 1) / 2;
@@ -52,33 +36,21 @@ template <typename T, int K> struct AdjCfg {
   static constexpr int KKP = round_up(KK, VEC);
   static constexpr int VLB = KK <= 16 ? 16 : (KK <= 32 ? 32 : 64);
   static constexpr int TILE_ELEMS = SR * PITCH;
-  static __host__ size_t smem_bytes(int N) { return (size_t)(N * KKP + 2 * TILE_ELEMS) * sizeof(T); }
+  static __host__ size_t smem_bytes(int) { return (size_t)(2 * TILE_ELEMS) * sizeof(T); }
 };
 
 template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_kernel(const AdjParams<T> p) {
   using Cfg = AdjCfg<T, K>;
   constexpr int R = Cfg::R, NT = Cfg::NT, VEC = Cfg::VEC, RW = Cfg::RW, TW = Cfg::TW, TH = Cfg::TH;
-  constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK, KKP = Cfg::KKP;
+  constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK;
   constexpr int TILE = Cfg::TILE_ELEMS;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *wflip = reinterpret_cast<T *>(smem_raw); // [N][KKP]: wflip[n][a'*K+b'] = K_n[K-1-a'][K-1-b']
-  T *gbuf = wflip + p.N * KKP;                // [2][SR][PITCH]
+  T *gbuf = reinterpret_cast<T *>(smem_raw); // [2][SR][PITCH]
+  const T *cw = const_taps<T>(p.slot);       // [N][K][K] taps in constant memory (uniform operands)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, N = p.N, C = p.C;
-
-  for (int idx = tid; idx < N * KKP; idx += NT) {
-    const int n = idx / KKP, e = idx % KKP;
-    T w = T(0);
-    if (e < KK) {
-      if (p.kernels0)
-        w = n == 0 ? p.kernels0[KK - 1 - e] : p.kernels[(n - 1) * KK + (KK - 1 - e)];
-      else
-        w = p.kernels[n * KK + (KK - 1 - e)];
-    }
-    wflip[idx] = w;
-  }
 
   auto decode = [&](int item, int &b, int &c, int &ty, int &tx) {
     tx = item % p.tiles_x;
@@ -139,10 +111,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 
       // ---- B1: data gradient (correlation of g_n with the flipped filter)
       {
-        T wreg[KKP];
-#pragma unroll
-        for (int q = 0; q < KKP / VEC; ++q)
-          ld_vec(wflip + n * KKP + q * VEC, &wreg[q * VEC]);
+        const T *wn = cw + n * KK; // this filter's taps; flipped index below = transposed correlation
 #pragma unroll
         for (int rho = 0; rho < RW + K - 1; ++rho) {
           T row[NV * VEC];
@@ -157,7 +126,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
               const int j = rho - a;
               if (j >= 0 && j < RW) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) lacc[j][i] = fma_(wreg[a * K + bb], row[i + bb], lacc[j][i]);
+                for (int i = 0; i < VEC; ++i) lacc[j][i] = fma_(row[i + bb], wn[KK - 1 - (a * K + bb)], lacc[j][i]);
               }
             }
         }
@@ -215,20 +184,6 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 }
 
 // --------------------------------------------------------------------------------------------
-template <typename T> struct FGradParams {
-  const T *g; // [B][C*N][g_rows][W]
-  int g_rows, g_off;
-  const T *u; // [B][C][u_rows][W]
-  int u_rows, u_off;
-  int wrap_y;
-  double *dk_partial; // [gridDim.x * 6][N][VLB], accumulated across launches
-  int n0, nw;         // this launch handles filters n0 .. n0+nw-1; warp w -> filter n0 + w % nw,
-                      // row part w / nw of `parts` = NWARPS / nw (nw divides NWARPS)
-  int vec_ok;         // 1 if g rows may be read with 16-byte loads (W % VEC == 0, base aligned)
-  int B, C, N, H, W;
-  int tiles_x, tiles_y, n_items;
-};
-
 template <typename T, int K> struct FGradCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int VEC = VecOf<T>::N;
@@ -347,16 +302,18 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
           T row[NV * VEC];
 #pragma unroll
           for (int v = 0; v < NV; ++v) ld_vec(um + rho * PITCH + v * VEC, &row[v * VEC]);
+          // column of the micro-tile outermost: every accumulator is touched once per pass, so
+          // dependent FMAs are ~K*K instructions apart
 #pragma unroll
-          for (int a = 0; a < K; ++a) {
-            const int j = rho - a;
-            if (j >= 0 && j < RW) {
+          for (int i = 0; i < VEC; ++i)
 #pragma unroll
-              for (int i = 0; i < VEC; ++i)
+            for (int a = 0; a < K; ++a) {
+              const int j = rho - a;
+              if (j >= 0 && j < RW) {
 #pragma unroll
                 for (int bb = 0; bb < K; ++bb) kacc[a * K + bb] = fma_(gc[j][i], row[i + bb], kacc[a * K + bb]);
+              }
             }
-          }
         }
       }
     }
@@ -380,26 +337,6 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
       if ((lane % DUP) == 0 && e < KK) slot[e] += (double)kacc[0];
     }
   }
-}
-
-// ---- tiny deterministic finishing kernels ----------------------------------------------------
-// out[n*KK + e] = sum over slots of partial[slot][n][e]   (fixed order)
-template <typename T>
-__global__ void reduce_dk_kernel(const double *partial, int n_slots, int N, int KK, int VLB, T *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * KK) return;
-  const int n = i / KK, e = i % KK;
-  double s = 0.0;
-  for (int sl = 0; sl < n_slots; ++sl) s += partial[((size_t)sl * N + n) * VLB + e];
-  out[i] = (T)s;
-}
-// out[i] = sum over slots of partial[slot][i]
-template <typename T> __global__ void reduce_flat_kernel(const double *partial, int n_slots, int n, T *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int sl = 0; sl < n_slots; ++sl) s += partial[(size_t)sl * n + i];
-  out[i] = (T)s;
 }
 
 } // namespace pdenet

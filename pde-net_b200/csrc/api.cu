@@ -2,10 +2,12 @@
 // everything is ordered on the caller's stream.
 #include "../../include/pdenet_b200.h"
 #include "launch.cuh"
+#include "small_kernels.cuh"
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace pdenet {
@@ -49,6 +51,7 @@ struct ProfScope {
 #define PDENET_EXTERN(TT, KK)                                                                                     \
   extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
   extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, cudaStream_t);                          \
+  extern template int upload_taps<TT, KK>(int, int, const TT *, int, cudaStream_t);                              \
   extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, cudaStream_t);                    \
   extern template void filter_grad_tile<TT, KK>(int &, int &);                                                   \
   extern template int adjoint_vlb<TT, KK>();                                                                     \
@@ -56,6 +59,38 @@ struct ProfScope {
 PDENET_EXTERN(double, 3) PDENET_EXTERN(double, 5) PDENET_EXTERN(double, 7)
 PDENET_EXTERN(float, 3) PDENET_EXTERN(float, 5) PDENET_EXTERN(float, 7)
 #undef PDENET_EXTERN
+
+// ---------------------------------------------------------------------------------------------
+// Ring of constant-memory tap slots (see common.cuh).  A call takes the next slot, makes its
+// stream wait for the slot's previous user, uploads its taps (stream-ordered device-to-device
+// copy into the __constant__ bank of the matching translation unit) and records the slot's event
+// after its last kernel.  This is the library's only cross-call state.
+struct SlotRing {
+  std::mutex m;
+  int next = 0;
+  cudaEvent_t ev[16][kConstSlots];
+  bool have[16] = {false};
+};
+static SlotRing g_slots;
+
+struct SlotLease {
+  int slot = -1, dev = 0;
+  cudaStream_t st;
+  explicit SlotLease(cudaStream_t s) : st(s) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
+    std::lock_guard<std::mutex> lk(g_slots.m);
+    if (!g_slots.have[dev]) {
+      for (int i = 0; i < kConstSlots; ++i) cudaEventCreateWithFlags(&g_slots.ev[dev][i], cudaEventDisableTiming);
+      g_slots.have[dev] = true;
+    }
+    slot = g_slots.next;
+    g_slots.next = (g_slots.next + 1) % kConstSlots;
+    cudaStreamWaitEvent(st, g_slots.ev[dev][slot], 0);
+  }
+  ~SlotLease() {
+    if (slot >= 0) cudaEventRecord(g_slots.ev[dev][slot], st);
+  }
+};
 
 #define PDENET_DISPATCH_K(k, EXPR)                                                                                \
   switch (k) {                                                                                                    \
@@ -209,6 +244,20 @@ static int sandwich(int which, const T *in, const double *scale_host, const unsi
 }
 
 // ---------------------------------------------------------------------------------------------
+// upload [n][k][k] taps (optionally preceded by one extra filter k0) into a leased constant slot
+template <typename T>
+static int upload(const SlotLease &lease, const T *k0, const T *taps, int n, int k, cudaStream_t st) {
+  if (lease.slot < 0) return PDENET_E_CUDA;
+  int rc = 0, first = 0;
+  if (k0) {
+    PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, 0, k0, 1, st)));
+    if (rc) return rc;
+    first = 1;
+  }
+  PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, first, taps, n, st)));
+  return rc;
+}
+
 static bool bad_geom(int B, int C, int H, int W, int k, int N) {
   return B <= 0 || C <= 0 || H <= 0 || W <= 0 || k <= 0 || (k % 2) == 0 || N <= 0;
 }
@@ -291,9 +340,11 @@ static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states
     return PDENET_E_BADARG;
   if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
   const size_t stride = (size_t)B * C * H * W;
+  SlotLease lease((cudaStream_t)stream);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, (cudaStream_t)stream)) return rc;
   StepParams<T> p;
   memset(&p, 0, sizeof(p));
-  p.kernels = kernels;
+  p.slot = lease.slot;
   p.symnet = symnet;
   p.L = L;
   p.Psym = symnet_param_count(C * N, L);
@@ -314,9 +365,11 @@ template <typename T>
 static int fd2d_fwd(const T *u, const T *kernels, T *feats, int B, int C, int H, int W, int k, int N, void *stream) {
   if (!u || !kernels || !feats || bad_geom(B, C, H, W, k, N)) return PDENET_E_BADARG;
   if (!nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  SlotLease lease((cudaStream_t)stream);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, (cudaStream_t)stream)) return rc;
   StepParams<T> p;
   memset(&p, 0, sizeof(p));
-  p.kernels = kernels;
+  p.slot = lease.slot;
   p.symnet = kernels; // unused in MODE_FEATS (Psym = 0)
   p.wrap_y = 1;
   p.u_rows = p.out_rows = H;
@@ -340,6 +393,8 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
   cudaStream_t st = (cudaStream_t)stream;
   double *dkp = (double *)workspace;
   if (grad_kernels && cudaMemsetAsync(dkp, 0, need, st) != cudaSuccess) return PDENET_E_CUDA;
+  SlotLease lease(st);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, st)) return rc;
   AdjParams<T> q;
   memset(&q, 0, sizeof(q));
   q.g = grad_feats;
@@ -347,7 +402,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
   q.wrap_y = 1;
   q.lam_out = grad_u;
   q.lo_rows = H;
-  q.kernels = kernels;
+  q.slot = lease.slot;
   int rc = 0;
   if (grad_u) {
     PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, C, N, H, W, st)));
@@ -378,9 +433,11 @@ static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *o
       out_rows < Hs + out_off || out_off < 0)
     return PDENET_E_BADARG;
   if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  SlotLease lease((cudaStream_t)stream);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, (cudaStream_t)stream)) return rc;
   StepParams<T> p;
   memset(&p, 0, sizeof(p));
-  p.kernels = kernels;
+  p.slot = lease.slot;
   p.symnet = symnet;
   p.L = L;
   p.Psym = symnet_param_count(C * N, L);
@@ -453,6 +510,8 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
       cudaMemsetAsync(symp, 0, (size_t)lay.sym_slots * C * Psym * sizeof(double), st) != cudaSuccess)
     return PDENET_E_CUDA;
 
+  SlotLease lease(st);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, st)) return rc;
   const size_t img = (size_t)H * W;
   const size_t stride = (size_t)B * C * img;
   const T *lam_in = grad_mode == PDENET_GRAD_ALL ? grad_states + (size_t)(steps - 1) * stride : grad_states;
@@ -466,7 +525,7 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
       const size_t boff = (size_t)b0 * C * img;
       StepParams<T> p;
       memset(&p, 0, sizeof(p));
-      p.kernels = kernels;
+      p.slot = lease.slot;
       p.symnet = symnet;
       p.L = L;
       p.Psym = Psym;
@@ -494,7 +553,7 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
         q.inj_rows = H;
         q.lam_out = lam_out + boff;
         q.lo_rows = H;
-        q.kernels = kernels;
+        q.slot = lease.slot;
         PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, nb, C, N, H, W, st)));
         if (rc) return rc;
       }
@@ -536,10 +595,11 @@ static int linear_fwd(const T *u0, const T *id_kernel, const T *kernels, const T
     return PDENET_E_BADARG;
   if (!lin_supported(N + 1)) return PDENET_E_UNSUPPORTED;
   const size_t stride = (size_t)B * H * W;
+  SlotLease lease((cudaStream_t)stream);
+  if (int rc = upload<T>(lease, id_kernel, kernels, N, k, (cudaStream_t)stream)) return rc;
   StepParams<T> p;
   memset(&p, 0, sizeof(p));
-  p.kernels = kernels;
-  p.kernels0 = id_kernel;
+  p.slot = lease.slot;
   p.symnet = coe;
   p.dt = (T)dt;
   p.wrap_y = 1;
@@ -613,6 +673,8 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * (N + 1) * lay.vlb * sizeof(double), st) != cudaSuccess ||
       cudaMemsetAsync(dcoe, 0, (size_t)B * N * img * sizeof(T), st) != cudaSuccess)
     return PDENET_E_CUDA;
+  SlotLease lease(st);
+  if (int rc = upload<T>(lease, id_kernel, kernels, N, k, st)) return rc;
   const T *lam_in = grad_mode == PDENET_GRAD_ALL ? grad_states + (size_t)(steps - 1) * stride : grad_states;
   int cur = 0;
   for (int t = steps - 1; t >= 0; --t) {
@@ -621,8 +683,7 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
     const T *inject = (grad_mode == PDENET_GRAD_ALL && t > 0) ? grad_states + (size_t)(t - 1) * stride : nullptr;
     StepParams<T> p;
     memset(&p, 0, sizeof(p));
-    p.kernels = kernels;
-    p.kernels0 = id_kernel;
+    p.slot = lease.slot;
     p.symnet = coe;
     p.dt = (T)dt;
     p.wrap_y = 1;
@@ -647,8 +708,7 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
       q.inj_rows = H;
       q.lam_out = lam_out;
       q.lo_rows = H;
-      q.kernels = kernels;
-      q.kernels0 = id_kernel;
+      q.slot = lease.slot;
       PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, 1, N + 1, H, W, st)));
       if (rc) return rc;
     }
@@ -702,6 +762,37 @@ template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T *
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += x[i];
   if (s == (T)123456789) out[0] = s; // never true; keeps the loop alive
+}
+
+// operand-pattern probes: 16 accumulators, 16 + 16 multiplicands kept in registers
+template <typename T, int VARIANT> __global__ void __launch_bounds__(256) fma_probe_kernel(T *out, int iters) {
+  T x[16], y[16], z[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    x[i] = (T)(threadIdx.x + i) * (T)1e-3;
+    y[i] = (T)0.999 + (T)i * (T)1e-6;
+    z[i] = (T)1e-3 * (T)(i + 1);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (VARIANT == 1) x[i] = fma_(y[(i + r) & 15], z[(i + 3 * r + 1) & 15], x[i]);
+        if (VARIANT == 2) x[i] = fma_(y[(i + r) & 15], z[((i >> 2) + r) & 15], x[i]);
+      }
+    if (it == iters + 1) { // never true: keeps y, z live as variables
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        y[i] += x[i];
+        z[i] += x[i];
+      }
+    }
+  }
+  T s = T(0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == (T)123456789) out[0] = s;
 }
 
 } // namespace pdenet
@@ -890,7 +981,12 @@ int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind) {
 }
 
 int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream) {
-  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out) return PDENET_E_BADARG;
+  return pdenet_fma_probe(elem_size, iters, 0, flops_out, ms_out, stream);
+}
+
+int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream) {
+  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out || variant < 0 || variant > 2)
+    return PDENET_E_BADARG;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
@@ -902,10 +998,15 @@ int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, 
   const int grid = sms * 8, block = 256;
   for (int rep = 0; rep < 2; ++rep) { // first pass warms up
     cudaEventRecord(e0, st);
-    if (elem_size == 8)
-      fma_peak_kernel<double><<<grid, block, 0, st>>>((double *)scratch, iters, 0.999, 1e-3);
-    else
-      fma_peak_kernel<float><<<grid, block, 0, st>>>((float *)scratch, iters, 0.999f, 1e-3f);
+    if (elem_size == 8) {
+      if (variant == 0) fma_peak_kernel<double><<<grid, block, 0, st>>>((double *)scratch, iters, 0.999, 1e-3);
+      if (variant == 1) fma_probe_kernel<double, 1><<<grid, block, 0, st>>>((double *)scratch, iters);
+      if (variant == 2) fma_probe_kernel<double, 2><<<grid, block, 0, st>>>((double *)scratch, iters);
+    } else {
+      if (variant == 0) fma_peak_kernel<float><<<grid, block, 0, st>>>((float *)scratch, iters, 0.999f, 1e-3f);
+      if (variant == 1) fma_probe_kernel<float, 1><<<grid, block, 0, st>>>((float *)scratch, iters);
+      if (variant == 2) fma_probe_kernel<float, 2><<<grid, block, 0, st>>>((float *)scratch, iters);
+    }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
   }

@@ -8,6 +8,21 @@ namespace pdenet {
 constexpr int kMaxLayers = 8;   // PDENET_MAX_LAYERS
 constexpr int kMaxFilters = 16; // PDENET_MAX_FILTERS
 
+// Filter taps live in constant memory: a warp-uniform constant index lets the compiler fetch them
+// with LDCU into UNIFORM registers and issue `DFMA R, R, UR, R`, which needs only two vector
+// register operands.  Measured on B200 (tools/probes): a DFMA with three
+// distinct vector-register operands is register-bank limited to ~73 % of the pipe rate, with a
+// uniform-register operand it reaches ~95 %.  A small ring of slots (guarded by events on the
+// host side) keeps concurrent calls on different streams from overwriting each other's taps.
+constexpr int kConstSlots = 8;
+constexpr int kConstSlotBytes = kMaxFilters * 49 * 8; // up to 16 filters of 7x7 doubles
+#ifdef PDENET_DEFINE_CONST
+__constant__ __align__(16) unsigned char c_slots[kConstSlots * kConstSlotBytes];
+template <typename T> __device__ __forceinline__ const T *const_taps(int slot) {
+  return reinterpret_cast<const T *>(c_slots + slot * kConstSlotBytes);
+}
+#endif
+
 // 16-byte vector type per scalar type (LDS.128 / STG.128 granularity).
 template <typename T> struct VecOf;
 template <> struct VecOf<double> {

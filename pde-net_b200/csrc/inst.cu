@@ -1,5 +1,9 @@
 // One translation unit per (PDENET_T, PDENET_K): explicit instantiation of the launchers.
+#define PDENET_DEFINE_CONST
 #include "launch.cuh"
+
+#include "adjoint_kernels.cuh"
+#include "step_kernels.cuh"
 
 #ifndef PDENET_T
 #error "compile with -DPDENET_T=double|float -DPDENET_K=3|5|7"
@@ -79,6 +83,16 @@ template <typename T, int K> void filter_grad_tile(int &tw, int &th) {
   th = FGradCfg<T, K>::TH;
 }
 
+template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st) {
+  if (slot < 0 || slot >= kConstSlots || (size_t)(first + n_filters) * K * K * sizeof(T) > (size_t)kConstSlotBytes)
+    return -2;
+  const cudaError_t e =
+      cudaMemcpyToSymbolAsync(c_slots, taps, (size_t)n_filters * K * K * sizeof(T),
+                              (size_t)slot * kConstSlotBytes + (size_t)first * K * K * sizeof(T),
+                              cudaMemcpyDeviceToDevice, st);
+  return e == cudaSuccess ? 0 : -4;
+}
+
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
 template <typename T, int K> void adjoint_tile(int &tw, int &th) {
   tw = AdjCfg<T, K>::TW;
@@ -90,6 +104,7 @@ template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int
 template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, cudaStream_t);
 template void filter_grad_tile<PDENET_T, PDENET_K>(int &, int &);
 template int adjoint_vlb<PDENET_T, PDENET_K>();
+template int upload_taps<PDENET_T, PDENET_K>(int, int, const PDENET_T *, int, cudaStream_t);
 template void adjoint_tile<PDENET_T, PDENET_K>(int &, int &);
 
 } // namespace pdenet

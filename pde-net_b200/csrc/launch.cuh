@@ -1,7 +1,6 @@
 // Host-side launchers, instantiated once per (scalar type, filter size) translation unit.
 #pragma once
-#include "adjoint_kernels.cuh"
-#include "step_kernels.cuh"
+#include "params.cuh"
 
 namespace pdenet {
 
@@ -19,6 +18,8 @@ template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid,
 template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st);
 template <typename T, int K> void filter_grad_tile(int &tw, int &th);
 template <typename T, int K> int adjoint_vlb();
+// copy n_filters [K][K] filters (device memory) into constant slot `slot`, starting at filter index `first`
+template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st);
 template <typename T, int K> void adjoint_tile(int &tw, int &th);
 
 } // namespace pdenet

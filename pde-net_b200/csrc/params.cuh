@@ -1,0 +1,67 @@
+// Kernel parameter blocks and launch geometry shared by the kernels (inst.cu) and the C-ABI (api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pdenet {
+
+enum StepMode { MODE_FWD = 0, MODE_FEATS = 1, MODE_BWD_A = 2, MODE_LIN_FWD = 3, MODE_LIN_BWD_A = 4 };
+
+template <typename T> struct StepParams {
+  // input state [B][C][u_rows][W]
+  const T *u;
+  int u_rows, u_off, wrap_y;
+  int slot; // constant-memory slot holding the N scaled filters [N][K][K] (linear modes: filter 0 = D0)
+  const T *symnet;  // [C][Psym]            (linear modes: coe [N-1][H][W])
+  // forward output [B][C][out_rows][W] / features [B][C*N][out_rows][W]
+  T *out;
+  int out_rows, out_off;
+  // reverse: adjoint of the step's output [B][C][lam_rows][W]
+  const T *lam;
+  int lam_rows, lam_off;
+  // reverse: derivative adjoints g [B][C*N][g_rows][W]
+  T *g;
+  int g_rows, g_off;
+  double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
+  T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches
+  int B, H, W, L, Psym;
+  T dt;
+  int tiles_x, tiles_y, n_items;
+};
+
+// Threads per CTA: the forward-type kernels fit 168 registers when C*N <= 12, so they run 12
+// warps per SM; the reverse kernel A (and the widest banks) need up to 255 registers -> 8 warps.
+__host__ __device__ constexpr int step_threads(int mode, int M) {
+  return ((mode == MODE_FWD || mode == MODE_FEATS || mode == MODE_LIN_FWD) && M <= 12) ? 384 : 256;
+}
+
+template <typename T> struct AdjParams {
+  const T *g; // [B][C*N][g_rows][W]
+  int g_rows, g_off;
+  int wrap_y;
+  const T *lam_in; // [B][C][li_rows][W]; NULL = 0
+  int li_rows, li_off;
+  const T *inject; // [B][C][inj_rows][W]; NULL = none
+  int inj_rows, inj_off;
+  T *lam_out; // [B][C][lo_rows][W]; NULL = skip the data gradient
+  int lo_rows, lo_off;
+  int slot;           // constant-memory slot holding the N filters [N][K][K]
+  int vec_ok;         // 1: g may be staged in 16-byte units (W % VEC == 0, base 16-byte aligned)
+  int B, C, N, H, W;
+  int tiles_x, tiles_y, n_items;
+};
+
+template <typename T> struct FGradParams {
+  const T *g; // [B][C*N][g_rows][W]
+  int g_rows, g_off;
+  const T *u; // [B][C][u_rows][W]
+  int u_rows, u_off;
+  int wrap_y;
+  double *dk_partial; // [gridDim.x * 6][N][VLB], accumulated across launches
+  int n0, nw;         // this launch handles filters n0 .. n0+nw-1; warp w -> filter n0 + w % nw,
+                      // row part w / nw of `parts` = NWARPS / nw (nw divides NWARPS)
+  int vec_ok;         // 1 if g rows may be read with 16-byte loads (W % VEC == 0, base aligned)
+  int B, C, N, H, W;
+  int tiles_x, tiles_y, n_items;
+};
+
+} // namespace pdenet

@@ -9,33 +9,9 @@
 // fp64 DFMA peak).
 #pragma once
 #include "common.cuh"
+#include "params.cuh"
 
 namespace pdenet {
-
-enum StepMode { MODE_FWD = 0, MODE_FEATS = 1, MODE_BWD_A = 2, MODE_LIN_FWD = 3, MODE_LIN_BWD_A = 4 };
-
-template <typename T> struct StepParams {
-  // input state [B][C][u_rows][W]
-  const T *u;
-  int u_rows, u_off, wrap_y;
-  const T *kernels;  // [N][K][K] scaled
-  const T *kernels0; // linear modes: the order-(0,0) "identity" filter [K][K] = filter 0; `kernels` holds 1..N-1
-  const T *symnet;  // [C][Psym]            (linear modes: coe [N-1][H][W])
-  // forward output [B][C][out_rows][W] / features [B][C*N][out_rows][W]
-  T *out;
-  int out_rows, out_off;
-  // reverse: adjoint of the step's output [B][C][lam_rows][W]
-  const T *lam;
-  int lam_rows, lam_off;
-  // reverse: derivative adjoints g [B][C*N][g_rows][W]
-  T *g;
-  int g_rows, g_off;
-  double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
-  T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches
-  int B, H, W, L, Psym;
-  T dt;
-  int tiles_x, tiles_y, n_items;
-};
 
 // per-warp transpose scratch used by the SymNet parameter-gradient reduction (see transpose_sum)
 template <typename T> struct TransposeCfg {
@@ -43,12 +19,6 @@ template <typename T> struct TransposeCfg {
   static constexpr int PITCH = 32 + VEC; // elements per row; keeps rows 16-byte aligned
   static constexpr int ELEMS = 32 * PITCH;
 };
-
-// Threads per CTA: the forward-type kernels fit 168 registers when C*N <= 12, so they run 12
-// warps per SM; the reverse kernel A (and the widest banks) need up to 255 registers -> 8 warps.
-__host__ __device__ constexpr int step_threads(int mode, int M) {
-  return ((mode == MODE_FWD || mode == MODE_FEATS || mode == MODE_LIN_FWD) && M <= 12) ? 384 : 256;
-}
 
 template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
@@ -60,13 +30,12 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static constexpr int VEC = VecOf<T>::N;
   static constexpr int NP = round_up(N, VEC);
   static constexpr int M = C * N;
-  static constexpr int W_ELEMS = K * K * NP;
   static constexpr int TILE_ELEMS = C * SR * PITCH;
   static __host__ __device__ constexpr int sym_elems(int Psym) { return round_up(C * Psym, VEC); }
   // per-warp SymNet-gradient accumulators (double, first in shared memory so they stay aligned)
   static __host__ __device__ constexpr int grad_elems(int Psym) { return round_up(C * Psym, 2); }
   static __host__ size_t smem_bytes(int Psym, bool with_grad) {
-    size_t e = W_ELEMS + sym_elems(Psym) + 2 * TILE_ELEMS + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
+    size_t e = sym_elems(Psym) + 2 * TILE_ELEMS + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
     return e * sizeof(T) + (with_grad ? (size_t)(NT / 32) * grad_elems(Psym) * sizeof(double) + 64 * sizeof(int) : 0);
   }
 };
@@ -535,31 +504,20 @@ template <typename T, int K, int N, int C, int MODE, int VL, int LT>
 __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const StepParams<T> p) {
   using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
-  constexpr int PITCH = Cfg::PITCH, NP = Cfg::NP, M = Cfg::M, NT = Cfg::NT, VEC = Cfg::VEC;
+  constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
   constexpr bool WITH_GRAD = (MODE == MODE_BWD_A);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sgrad = reinterpret_cast<double *>(smem_raw); // [NT/32][grad_elems]  (MODE_BWD_A only)
-  T *ws = reinterpret_cast<T *>(sgrad + (WITH_GRAD ? (NT / 32) * Cfg::grad_elems(p.Psym) : 0)); // [K(b)][K(a)][NP]
-  T *syms = ws + Cfg::W_ELEMS;                                                                 // [C][Psym]
+  T *syms = reinterpret_cast<T *>(sgrad + (WITH_GRAD ? (NT / 32) * Cfg::grad_elems(p.Psym) : 0)); // [C][Psym]
+  const T *cw = const_taps<T>(p.slot); // [N][K][K] filter taps in constant memory (uniform operands)
   T *tiles = syms + (LINEAR ? 0 : Cfg::sym_elems(p.Psym)); // [2][C][SR][PITCH]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, L = p.L, Psym = p.Psym;
 
   // ---- one-time setup: weights (tap-major, filters innermost) and SymNet parameters
-  for (int idx = tid; idx < Cfg::W_ELEMS; idx += NT) {
-    const int n = idx % NP, ab = idx / NP, a = ab % K, b = ab / K;
-    T w = T(0);
-    if (n < N) {
-      if (LINEAR)
-        w = n == 0 ? p.kernels0[a * K + b] : p.kernels[((n - 1) * K + a) * K + b];
-      else
-        w = p.kernels[(n * K + a) * K + b];
-    }
-    ws[idx] = w;
-  }
   if (!LINEAR)
     for (int idx = tid; idx < Cfg::sym_elems(Psym); idx += NT) syms[idx] = idx < C * Psym ? p.symnet[idx] : T(0);
   if (WITH_GRAD)
@@ -631,19 +589,14 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
           T win[P + K - 1];
 #pragma unroll
           for (int i = 0; i < P + K - 1; ++i) win[i] = ut[i * PITCH + bb];
-          const T *wb = ws + bb * K * NP;
 #pragma unroll
-          for (int a = 0; a < K; ++a) {
-            T wv[NP];
-#pragma unroll
-            for (int q = 0; q < NP / VEC; ++q) ld_vec(wb + a * NP + q * VEC, &wv[q * VEC]);
+          for (int a = 0; a < K; ++a)
 #pragma unroll
             for (int n = 0; n < N; ++n) {
-              const T w = wv[n];
+              const T w = cw[(n * K + a) * K + bb]; // warp-uniform -> LDCU + uniform-register operand
 #pragma unroll
-              for (int j = 0; j < P; ++j) acc[n][j] = fma_(w, win[j + a], acc[n][j]);
+              for (int j = 0; j < P; ++j) acc[n][j] = fma_(win[j + a], w, acc[n][j]);
             }
-          }
         }
 #pragma unroll
         for (int n = 0; n < N; ++n)

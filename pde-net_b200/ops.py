@@ -279,11 +279,13 @@ def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, 
     return out
 
 
-def fma_peak(dtype=torch.float64, iters: int = 4096):
-    """Measured CUDA-core FMA throughput in FLOP/s (register-only loop)."""
+def fma_peak(dtype=torch.float64, iters: int = 4096, variant: int = 0):
+    """Measured CUDA-core FMA throughput in FLOP/s (register-only loop).  ``variant`` selects the
+    operand pattern (0: loop-invariant multiplicands, 1: three distinct register operands per FMA,
+    2: one operand shared by four consecutive FMAs)."""
     flops, ms = C.c_double(0), C.c_float(0)
-    _lib.check(_lib.lib().pdenet_fma_peak(8 if dtype == torch.float64 else 4, iters, C.byref(flops), C.byref(ms),
-                                          _stream()), "pdenet_fma_peak")
+    _lib.check(_lib.lib().pdenet_fma_probe(8 if dtype == torch.float64 else 4, iters, variant, C.byref(flops),
+                                           C.byref(ms), _stream()), "pdenet_fma_probe")
     return flops.value / (ms.value * 1e-3)
 
 
