@@ -161,7 +161,7 @@ def oracle_pass(sample, threads):
     return B * H * W * blocks / dt, dt
 
 
-CPU_SAMPLE = dict(B=8, H=1024, W=1024, blocks=2)
+CPU_SAMPLE = dict(B=8, H=1024, W=1024, blocks=4)
 
 
 def cpu_baseline(threads):
@@ -275,6 +275,10 @@ def run_ours(args):
 
     # FP64 CUDA-core peak on this GPU, this run (register-only DFMA loop)
     fma_peak = ops.fma_peak(dtype, 2048)
+    # operand-pattern probes: register-bank limit of a 3-vector-operand DFMA
+    fma_probe = {"loop_invariant_operands": fma_peak / 1e12,
+                 "three_distinct_vector_operands": ops.fma_peak(dtype, 2048, 1) / 1e12,
+                 "one_operand_shared_by_4": ops.fma_peak(dtype, 2048, 2) / 1e12}
 
     for _ in range(max(args.warmup, 3)):
         one_pass(u0)
@@ -356,7 +360,7 @@ def run_ours(args):
             "achieved": achieved, "peak": fma_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fma_peak / 1e12),
             "peak_source": "measured this run: pdenet_fma_peak register-only DFMA loop (nominal %.0f)" % NOMINAL_FP64_TFLOPS,
             "flops_per_launch": KERNEL_FLOPS[top] * pts_per_launch, "ms_per_launch": ms_top, "launches": n_top,
-            "traffic": traffic, "per_kernel": per_kernel,
+            "traffic": traffic, "per_kernel": per_kernel, "fma_probe_tflops": fma_probe,
             "kernel_ms_share": {kk: (v / total_kernel_ms if total_kernel_ms else None) for kk, v in kind_ms.items()},
             "whole_pass": {"flop_per_point_step": F_TOTAL, "achieved_tflops": F_TOTAL * value / 1e12 / world,
                            "frac_of_fp64_peak": F_TOTAL * value / world / fma_peak,
