@@ -148,6 +148,29 @@ PDENET_API int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels
                              int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
                              int N, int L, double dt, void *stream);
 
+/* Reverse of one slab step.  u_ext: state at the step's input, [B,C,Hs+4r,W] with 2r ghost rows
+ * on each side (r = (k-1)/2); lam_ext: adjoint of the step's output INCLUDING this step's loss
+ * seed, [B,C,Hs+2r,W] with r ghost rows on each side.  Writes the adjoint of the step's input for
+ * the Hs owned rows into lam_out (rows [out_row_offset, out_row_offset+Hs) of a buffer with
+ * out_rows_per_image rows per image) and accumulates this rank's filter / SymNet gradient partials
+ * (owned rows only) in the workspace: call _begin once, _step_bwd per step (last to first), _end once,
+ * then sum grad_kernels / grad_symnet over the ranks. */
+PDENET_API size_t pdenet_slab_bwd_workspace_bytes(int elem_size, int B, int C, int Hs, int W, int k, int N, int L);
+PDENET_API int pdenet_slab_bwd_begin(void *workspace, size_t workspace_bytes, int elem_size, int B, int C, int Hs, int W,
+                          int k, int N, int L, void *stream);
+PDENET_API int pdenet_slab_step_bwd_f64(const double *u_ext, const double *lam_ext, const double *kernels,
+                             const double *symnet, double *lam_out, int out_rows_per_image, int out_row_offset,
+                             void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
+                             int L, double dt, void *stream);
+PDENET_API int pdenet_slab_step_bwd_f32(const float *u_ext, const float *lam_ext, const float *kernels,
+                             const float *symnet, float *lam_out, int out_rows_per_image, int out_row_offset,
+                             void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
+                             int L, double dt, void *stream);
+PDENET_API int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *grad_kernels, double *grad_symnet,
+                            int B, int C, int Hs, int W, int k, int N, int L, void *stream);
+PDENET_API int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet,
+                            int B, int C, int Hs, int W, int k, int N, int L, void *stream);
+
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
  * 2 = reverse kernel B1 (data gradient), 3 = reverse kernel B2 (filter gradient),

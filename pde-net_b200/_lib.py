@@ -36,6 +36,10 @@ _PROTOS = {
     "pdenet_linear_rollout_bwd_workspace_bytes": (_sz, [_i] * 6),
     "pdenet_linear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 8 + [_sz] + [_i] * 6 + [_d, _vp]),
     "pdenet_slab_step_fwd_{t}": (_i, [_vp] * 4 + [_i] * 10 + [_d, _vp]),
+    "pdenet_slab_bwd_workspace_bytes": (_sz, [_i] * 8),
+    "pdenet_slab_bwd_begin": (_i, [_vp, _sz] + [_i] * 8 + [_vp]),
+    "pdenet_slab_step_bwd_{t}": (_i, [_vp] * 5 + [_i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
+    "pdenet_slab_bwd_end_{t}": (_i, [_vp, _sz, _vp, _vp] + [_i] * 7 + [_vp]),
     "pdenet_profile_enable": (_i, [_i]),
     "pdenet_profile_read": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "pdenet_fma_peak": (_i, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float), _vp]),

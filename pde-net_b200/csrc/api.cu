@@ -454,6 +454,129 @@ static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *o
   return rc;
 }
 
+// ---- reverse slab step (config 5) ------------------------------------------------
+struct SlabLayout {
+  size_t off_g, off_dk, off_sym, total;
+  int dk_slots, sym_slots, vlb;
+};
+static SlabLayout slab_layout(size_t es, int B, int C, int Hs, int W, int k, int N, int L, int sms) {
+  SlabLayout l;
+  const int kk = k * k, r = (k - 1) / 2;
+  l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
+  l.dk_slots = dk_slot_count(sms);
+  l.sym_slots = sms;
+  size_t o = 0;
+  l.off_g = o;
+  o = align_up(o + (size_t)B * C * N * (Hs + 2 * r) * W * es, 256);
+  l.off_dk = o;
+  o = align_up(o + (size_t)l.dk_slots * N * l.vlb * sizeof(double), 256);
+  l.off_sym = o;
+  o = align_up(o + (size_t)l.sym_slots * C * symnet_param_count(C * N, L) * sizeof(double), 256);
+  l.total = o;
+  return l;
+}
+
+template <typename T>
+static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, const T *symnet, T *lam_out,
+                         int out_rows, int out_off, void *workspace, size_t ws_bytes, int B, int C, int Hs, int W,
+                         int k, int N, int L, double dt, void *stream) {
+  if (!u_ext || !lam_ext || !kernels || !symnet || !lam_out || !workspace || bad_geom(B, C, Hs, W, k, N) || L < 0 ||
+      out_off < 0 || out_rows < Hs + out_off)
+    return PDENET_E_BADARG;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  const int M = C * N, VL = pick_vl(M, L), r = (k - 1) / 2;
+  if (!VL) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const SlabLayout lay = slab_layout(sizeof(T), B, C, Hs, W, k, N, L, sms);
+  if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
+  char *ws = (char *)workspace;
+  T *gbuf = (T *)(ws + lay.off_g);
+  SlotLease lease(st);
+  if (int rc = upload<T>(lease, nullptr, kernels, N, k, st)) return rc;
+  // kernel A on the owned rows (with parameter gradients) and on the r ghost rows above / below
+  // (g only): B1 needs g on [-r, Hs + r)
+  const int row0[3] = {0, -r, Hs}, nrows[3] = {Hs, r, r};
+  for (int part = 0; part < 3; ++part) {
+    if (nrows[part] <= 0) continue;
+    StepParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.slot = lease.slot;
+    p.symnet = symnet;
+    p.L = L;
+    p.Psym = symnet_param_count(M, L);
+    p.dt = (T)dt;
+    p.wrap_y = 0;
+    p.u = u_ext;
+    p.u_rows = Hs + 4 * r;
+    p.u_off = 2 * r + row0[part];
+    p.lam = lam_ext;
+    p.lam_rows = Hs + 2 * r;
+    p.lam_off = r + row0[part];
+    p.g = gbuf;
+    p.g_rows = Hs + 2 * r;
+    p.g_off = r + row0[part];
+    p.sym_partial = (double *)(ws + lay.off_sym);
+    p.skip_sym_grad = part != 0;
+    int rc = 0;
+    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_BWD_A, N, C, VL, p, B, nrows[part], W, st)));
+    if (rc) return rc;
+  }
+  AdjParams<T> q;
+  memset(&q, 0, sizeof(q));
+  q.g = gbuf;
+  q.g_rows = Hs + 2 * r;
+  q.g_off = r;
+  q.wrap_y = 0;
+  q.lam_in = lam_ext;
+  q.li_rows = Hs + 2 * r;
+  q.li_off = r;
+  q.lam_out = lam_out;
+  q.lo_rows = out_rows;
+  q.lo_off = out_off;
+  q.slot = lease.slot;
+  int rc = 0;
+  PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, C, N, Hs, W, st)));
+  if (rc) return rc;
+  FGradParams<T> f;
+  memset(&f, 0, sizeof(f));
+  f.g = gbuf;
+  f.g_rows = Hs + 2 * r;
+  f.g_off = r;
+  f.u = u_ext;
+  f.u_rows = Hs + 4 * r;
+  f.u_off = 2 * r;
+  f.wrap_y = 0;
+  f.dk_partial = (double *)(ws + lay.off_dk);
+  PDENET_DISPATCH_K(k, rc = (run_filter_grad<T, KK_>(f, B, C, N, Hs, W, st)));
+  return rc;
+}
+
+template <typename T>
+static int slab_bwd_end(void *workspace, size_t ws_bytes, T *grad_kernels, T *grad_symnet, int B, int C, int Hs,
+                        int W, int k, int N, int L, void *stream) {
+  if (!workspace || bad_geom(B, C, Hs, W, k, N) || L < 0) return PDENET_E_BADARG;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const SlabLayout lay = slab_layout(sizeof(T), B, C, Hs, W, k, N, L, sms);
+  if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
+  char *ws = (char *)workspace;
+  if (grad_kernels) {
+    const int n = N * k * k;
+    ProfScope ps(4, st);
+    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>((double *)(ws + lay.off_dk), lay.dk_slots, N, k * k, lay.vlb,
+                                                         grad_kernels);
+  }
+  if (grad_symnet) {
+    const int n = C * symnet_param_count(C * N, L);
+    ProfScope ps(4, st);
+    reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>((double *)(ws + lay.off_sym), lay.sym_slots, n, grad_symnet);
+  }
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
 // ---- reverse rollout (row a11) ---------------------------------------------------------------
 struct BwdLayout {
   size_t off_g, off_lam0, off_lam1, off_dk, off_sym, total;
@@ -954,6 +1077,48 @@ int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const flo
                              int L, double dt, void *st) {
   return slab_step_fwd<float>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset, k,
                               N, L, dt, st);
+}
+
+size_t pdenet_slab_bwd_workspace_bytes(int elem_size, int B, int C, int Hs, int W, int k, int N, int L) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, C, Hs, W, k, N) || L < 0) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  return slab_layout((size_t)elem_size, B, C, Hs, W, k, N, L, sms).total;
+}
+int pdenet_slab_bwd_begin(void *workspace, size_t workspace_bytes, int elem_size, int B, int C, int Hs, int W, int k,
+                          int N, int L, void *stream) {
+  if (!workspace || (elem_size != 4 && elem_size != 8) || bad_geom(B, C, Hs, W, k, N) || L < 0)
+    return PDENET_E_BADARG;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const SlabLayout lay = slab_layout((size_t)elem_size, B, C, Hs, W, k, N, L, sms);
+  if (workspace_bytes < lay.total) return PDENET_E_WORKSPACE;
+  char *ws = (char *)workspace;
+  return cudaMemsetAsync(ws + lay.off_dk, 0, lay.total - lay.off_dk, (cudaStream_t)stream) == cudaSuccess
+             ? PDENET_OK
+             : PDENET_E_CUDA;
+}
+int pdenet_slab_step_bwd_f64(const double *u_ext, const double *lam_ext, const double *kernels,
+                             const double *symnet, double *lam_out, int out_rows_per_image, int out_row_offset,
+                             void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
+                             int L, double dt, void *st) {
+  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, out_rows_per_image, out_row_offset,
+                               workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
+}
+int pdenet_slab_step_bwd_f32(const float *u_ext, const float *lam_ext, const float *kernels, const float *symnet,
+                             float *lam_out, int out_rows_per_image, int out_row_offset, void *workspace,
+                             size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                             void *st) {
+  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, out_rows_per_image, out_row_offset, workspace,
+                              workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
+}
+int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *grad_kernels, double *grad_symnet, int B,
+                            int C, int Hs, int W, int k, int N, int L, void *st) {
+  return slab_bwd_end<double>(workspace, workspace_bytes, grad_kernels, grad_symnet, B, C, Hs, W, k, N, L, st);
+}
+int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet, int B,
+                            int C, int Hs, int W, int k, int N, int L, void *st) {
+  return slab_bwd_end<float>(workspace, workspace_bytes, grad_kernels, grad_symnet, B, C, Hs, W, k, N, L, st);
 }
 
 int pdenet_profile_enable(int on) {

@@ -22,6 +22,7 @@ template <typename T> struct StepParams {
   T *g;
   int g_rows, g_off;
   double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
+  int skip_sym_grad;   // 1: ghost-row launch of a slab -- emit g only, contribute no parameter gradient
   T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches
   int B, H, W, L, Psym;
   T dt;

@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
       double tot = 0.0;
 #pragma unroll
       for (int w = 0; w < NT / 32; ++w) tot += sgrad[w * Cfg::grad_elems(Psym) + idx];
-      p.sym_partial[(size_t)blockIdx.x * CP + idx] += tot;
+      if (!p.skip_sym_grad) p.sym_partial[(size_t)blockIdx.x * CP + idx] += tot;
     }
   }
 }

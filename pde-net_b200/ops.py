@@ -279,6 +279,50 @@ def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, 
     return out
 
 
+class SlabBackward:
+    """Reverse pass of a slab-decomposed rollout on one rank (C-ABI pdenet_slab_*bwd*).
+
+    ``step(u_ext2, lam_ext, lam_out)`` is called once per step, last to first, with the step's
+    input state extended by 2r ghost rows and the adjoint of its output (seed included) extended by
+    r ghost rows; ``finish()`` returns this rank's (grad_kernels, grad_symnet) contribution."""
+
+    def __init__(self, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, B: int, C: int, Hs: int,
+                 W: int):
+        self.kernels = _req(kernels.detach(), "kernels")
+        self.symnet = _req(symnet.detach(), "symnet", self.kernels.dtype)
+        self.L, self.dt = int(L), float(dt)
+        self.B, self.C, self.Hs, self.W = B, C, Hs, W
+        self.N, self.k = self.kernels.shape[0], self.kernels.shape[-1]
+        self.r = (self.k - 1) // 2
+        es = self.kernels.element_size()
+        self.nbytes = _lib.lib().pdenet_slab_bwd_workspace_bytes(es, B, C, Hs, W, self.k, self.N, self.L)
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=self.kernels.device)
+        _lib.check(_lib.lib().pdenet_slab_bwd_begin(_ptr(self.ws), self.nbytes, es, B, C, Hs, W, self.k, self.N, self.L,
+                                                    _stream()), "pdenet_slab_bwd_begin")
+
+    def step(self, u_ext2: torch.Tensor, lam_ext: torch.Tensor, lam_out: torch.Tensor, out_row_offset: int = 0):
+        dt_ = self.kernels.dtype
+        u_ext2, lam_ext = _req(u_ext2, "u_ext2", dt_), _req(lam_ext, "lam_ext", dt_)
+        if tuple(u_ext2.shape) != (self.B, self.C, self.Hs + 4 * self.r, self.W):
+            raise ValueError("u_ext2 must carry 2r ghost rows on each side")
+        if tuple(lam_ext.shape) != (self.B, self.C, self.Hs + 2 * self.r, self.W):
+            raise ValueError("lam_ext must carry r ghost rows on each side")
+        if not lam_out.is_contiguous():
+            raise ValueError("lam_out must be contiguous")
+        _lib.check(_lib.fn("pdenet_slab_step_bwd", dt_)(
+            _ptr(u_ext2), _ptr(lam_ext), _ptr(self.kernels), _ptr(self.symnet), _ptr(lam_out), lam_out.shape[2],
+            out_row_offset, _ptr(self.ws), self.nbytes, self.B, self.C, self.Hs, self.W, self.k, self.N, self.L,
+            self.dt, _stream()), "pdenet_slab_step_bwd")
+        return lam_out
+
+    def finish(self):
+        gk, gs = torch.empty_like(self.kernels), torch.empty_like(self.symnet)
+        _lib.check(_lib.fn("pdenet_slab_bwd_end", self.kernels.dtype)(
+            _ptr(self.ws), self.nbytes, _ptr(gk), _ptr(gs), self.B, self.C, self.Hs, self.W, self.k, self.N, self.L,
+            _stream()), "pdenet_slab_bwd_end")
+        return gk, gs
+
+
 def fma_peak(dtype=torch.float64, iters: int = 4096, variant: int = 0):
     """Measured CUDA-core FMA throughput in FLOP/s (register-only loop).  ``variant`` selects the
     operand pattern (0: loop-invariant multiplicands, 1: three distinct register operands per FMA,

@@ -5,7 +5,9 @@
   moment / SymNet gradient (plus the loss) -- a few KB, latency-bound over NVLink/NVSwitch.
 * Slab domain decomposition (config 5): rows of one huge grid are split across ranks; before each
   step every rank fills its ghost rows from its ring neighbours (periodic in H makes it a true
-  ring) and calls the non-periodic slab step of the C-ABI.  Forward only in this round.
+  ring) and calls the non-periodic slab step of the C-ABI.  The reverse pass exchanges 2r ghost
+  rows of the stored state and r ghost rows of the adjoint per step, recomputes on the ghost
+  rows, and ends with the same flat all-reduce of the parameter gradients.
 
 The reference is single-process: nothing here replaces a reference interface.
 """
@@ -67,17 +69,20 @@ class SlabDecomposition:
         self.up = (rank - 1) % world      # owns the rows above (smaller y)
         self.down = (rank + 1) % world    # owns the rows below
 
-    def extend(self, u_local: torch.Tensor) -> torch.Tensor:
+    def extend(self, u_local: torch.Tensor, halo: Optional[int] = None) -> torch.Tensor:
         """[B,C,Hs,W] -> [B,C,Hs+2*halo,W] with the interior copied in (ghosts unset)."""
+        h = self.halo if halo is None else halo
         B, C, Hs, W = u_local.shape
-        ext = torch.empty(B, C, Hs + 2 * self.halo, W, dtype=u_local.dtype, device=u_local.device)
-        ext[:, :, self.halo:self.halo + Hs] = u_local
+        ext = torch.empty(B, C, Hs + 2 * h, W, dtype=u_local.dtype, device=u_local.device)
+        ext[:, :, h:h + Hs] = u_local
         return ext
 
-    def exchange(self, ext: torch.Tensor) -> None:
+    def exchange(self, ext: torch.Tensor, halo: Optional[int] = None) -> None:
         """Fill the ghost rows of ``ext`` in place: top ghosts <- bottom rows of `up`, bottom
         ghosts <- top rows of `down`.  One batched isend/irecv per neighbour."""
-        h, Hs = self.halo, self.Hs
+        h, Hs = (self.halo if halo is None else halo), self.Hs
+        if h > Hs:
+            raise ValueError("ghost zone wider than a slab: needs data beyond the ring neighbours")
         top_rows = ext[:, :, h:2 * h].contiguous()            # my first rows -> `up`'s bottom ghosts
         bot_rows = ext[:, :, Hs:Hs + h].contiguous()          # my last rows  -> `down`'s top ghosts
         if self.world == 1:
@@ -111,3 +116,41 @@ class SlabDecomposition:
             step_fn(a, kernels, symnet, L, dt, h, b, h)   # new interior lands inside the other buffer
             a, b = b, a
         return a[:, :, h:h + self.Hs].contiguous()
+
+    def rollout_fwd_bwd(self, u_local: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float,
+                        steps: int, grad_last_local: Callable, step_fn: Optional[Callable] = None,
+                        bwd_factory: Optional[Callable] = None):
+        """Forward rollout on this rank's slab, then the reverse pass.
+
+        ``grad_last_local(final_local) -> dLoss/d(final state)`` for the owned rows (the loss is
+        a sum over ranks of local terms).  Returns ``(final_local, grad_u0_local, grad_kernels,
+        grad_symnet)`` with the parameter gradients already summed over the ranks (one flat
+        all-reduce).  ``bwd_factory(kernels, symnet, L, dt, B, C, Hs, W)`` defaults to the CUDA
+        ``ops.SlabBackward``."""
+        from . import ops
+        if step_fn is None:
+            step_fn = ops.slab_step
+        if bwd_factory is None:
+            bwd_factory = ops.SlabBackward
+        h = self.halo
+        B, C, Hs, W = u_local.shape
+        states = [u_local]                       # owned rows of u_0 .. u_steps
+        a = self.extend(u_local)
+        for _ in range(steps):
+            self.exchange(a)
+            nxt = torch.empty_like(a)
+            step_fn(a, kernels, symnet, L, dt, h, nxt, h)
+            states.append(nxt[:, :, h:h + Hs].contiguous())
+            a = nxt
+        final = states[-1]
+        lam = grad_last_local(final).contiguous()
+        bwd = bwd_factory(kernels, symnet, L, dt, B, C, Hs, W)
+        for t in range(steps - 1, -1, -1):
+            u2 = self.extend(states[t], 2 * h)
+            self.exchange(u2, 2 * h)
+            lam_ext = self.extend(lam, h)
+            self.exchange(lam_ext, h)
+            lam = bwd.step(u2, lam_ext, torch.empty_like(lam))
+        gk, gs = bwd.finish()
+        flat_allreduce([gk, gs], group=self.group)
+        return final, lam, gk, gs

@@ -31,6 +31,10 @@ def _model(k=5, max_order=2, C=2, L=2, dx=0.3):
     return Ks, sym, u0
 
 
+def _weights(u0):
+    return torch.randn(u0.shape, generator=torch.Generator().manual_seed(17), dtype=torch.float64)
+
+
 def _oracle_slab_step(ext, Ks, sym, L, dt, halo, out, out_row_offset):
     """Non-periodic-in-H step on an extended slab, built from the oracle's periodic step: pad H
     periodically is wrong for a slab, so evaluate on the extended block and keep interior rows
@@ -39,6 +43,34 @@ def _oracle_slab_step(ext, Ks, sym, L, dt, halo, out, out_row_offset):
     full = O.step(ext, Ks, sym, L, dt)
     out[:, :, out_row_offset:out_row_offset + Hs] = full[:, :, halo:halo + Hs]
     return out
+
+
+class _OracleSlabBackward:
+    """CPU stand-in for ops.SlabBackward built from the oracle's autograd (same interface)."""
+
+    def __init__(self, Ks, sym, L, dt, B, C, Hs, W):
+        self.Ks, self.sym, self.L, self.dt, self.Hs = Ks, sym, L, dt, Hs
+        self.r = (Ks.shape[-1] - 1) // 2
+        self.gk, self.gs = torch.zeros_like(Ks), torch.zeros_like(sym)
+
+    def step(self, u_ext2, lam_ext, lam_out, out_row_offset=0):
+        r, Hs = self.r, self.Hs
+        u = u_ext2.clone().requires_grad_(True)
+        K, s = self.Ks.clone().requires_grad_(True), self.sym.clone().requires_grad_(True)
+        new = O.step(u, K, s, self.L, self.dt)           # rows within r of the block edge are wrap-contaminated
+        val = new[:, :, r:r + Hs + 2 * r]                 # logical rows [-r, Hs + r): clean
+        # data gradient: every row that reaches the owned rows contributes
+        gu, = torch.autograd.grad((val * lam_ext).sum(), u, retain_graph=True)
+        lam_out[:, :, out_row_offset:out_row_offset + Hs] = gu[:, :, 2 * r:2 * r + Hs]
+        # parameter gradients: owned rows only
+        own = (val[:, :, r:r + Hs] * lam_ext[:, :, r:r + Hs]).sum()
+        gk, gs = torch.autograd.grad(own, (K, s))
+        self.gk += gk
+        self.gs += gs
+        return lam_out
+
+    def finish(self):
+        return self.gk, self.gs
 
 
 def _worker(rank, world, port, q):
@@ -62,7 +94,11 @@ def _worker(rank, world, port, q):
         slab = PP.SlabDecomposition(u0.shape[2], 2, rank, world)
         mine = u0[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
         fin = slab.rollout(mine, Ks, sym, L, dt, steps, step_fn=_oracle_slab_step)
-        q.put((rank, Kc.grad, sc.grad, float(total), fin))
+        # ---- slab reverse pass: 2r / r ghost-row exchanges per step + flat all-reduce of the grads
+        wloc = _weights(u0)[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
+        fin2, gu0, sgk, sgs = slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, steps, lambda f: wloc,
+                                                   step_fn=_oracle_slab_step, bwd_factory=_OracleSlabBackward)
+        q.put((rank, Kc.grad, sc.grad, float(total), fin, fin2, gu0, sgk, sgs))
     finally:
         dist.destroy_process_group()
 
@@ -85,12 +121,20 @@ def test_dp_and_slab_world2():
     ref = O.rollout(u0, Kc, sc, L, dt, steps)[-1]
     loss = ref.square().sum() / u0[0].numel() / u0.shape[0]
     loss.backward()
-    for rank, gk, gs, tot, fin in res:
+    for rank, gk, gs, tot, fin, fin2, gu0, sgk, sgs in res:
         assert torch.allclose(gk, Kc.grad, rtol=1e-11, atol=1e-14)
         assert torch.allclose(gs, sc.grad, rtol=1e-11, atol=1e-14)
         assert abs(tot - float(loss)) < 1e-12 * max(1.0, abs(float(loss)))
     full = torch.cat([r[4] for r in res], dim=2)
     assert torch.allclose(full, ref, rtol=1e-12, atol=1e-13)
+    # slab reverse: stitched input gradient and all-reduced parameter gradients == single domain
+    u0r, K2, s2 = u0.clone().requires_grad_(True), Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    (O.rollout(u0r, K2, s2, L, dt, steps)[-1] * _weights(u0)).sum().backward()
+    assert torch.allclose(torch.cat([r[5] for r in res], dim=2), ref, rtol=1e-12, atol=1e-13)
+    assert torch.allclose(torch.cat([r[6] for r in res], dim=2), u0r.grad, rtol=1e-10, atol=1e-12)
+    for r_ in res:
+        assert torch.allclose(r_[7], K2.grad, rtol=1e-10, atol=1e-12)
+        assert torch.allclose(r_[8], s2.grad, rtol=1e-10, atol=1e-12)
 
 
 def test_shard_range_and_single_rank_slab():
