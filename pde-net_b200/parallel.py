@@ -91,10 +91,13 @@ class SlabDecomposition:
             return
         recv_top = torch.empty_like(top_rows)
         recv_bot = torch.empty_like(bot_rows)
+        # NCCL matches point-to-point operations between a pair of ranks by ORDER, not by tag: with
+        # two ranks `up` and `down` are the same peer, so the receives are posted in the order the
+        # peer sends (its first send, its top rows, is my bottom ghost zone).
         ops = [dist.P2POp(dist.isend, top_rows, self.up, self.group, tag=0),
                dist.P2POp(dist.isend, bot_rows, self.down, self.group, tag=1),
-               dist.P2POp(dist.irecv, recv_top, self.up, self.group, tag=1),
-               dist.P2POp(dist.irecv, recv_bot, self.down, self.group, tag=0)]
+               dist.P2POp(dist.irecv, recv_bot, self.down, self.group, tag=0),
+               dist.P2POp(dist.irecv, recv_top, self.up, self.group, tag=1)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         ext[:, :, :h] = recv_top
