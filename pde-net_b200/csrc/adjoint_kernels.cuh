@@ -23,7 +23,7 @@ template <typename T, int K> struct AdjCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = 256;
   static constexpr int VEC = VecOf<T>::N;
-  static constexpr int RW = 16;
+  static constexpr int RW = 8;
   static constexpr int TW = 32 * VEC, TH = RW * (NT / 32);
   // With 16-byte staging the tile is shifted left by XS columns so that the window start
   // (tile origin - R) is a multiple of VEC in global memory as well as in shared memory.
@@ -39,7 +39,7 @@ template <typename T, int K> struct AdjCfg {
   static __host__ size_t smem_bytes(int) { return (size_t)(2 * TILE_ELEMS) * sizeof(T); }
 };
 
-template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_kernel(const AdjParams<T> p) {
+template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_kernel(const AdjParams<T> p) {
   using Cfg = AdjCfg<T, K>;
   constexpr int R = Cfg::R, NT = Cfg::NT, VEC = Cfg::VEC, RW = Cfg::RW, TW = Cfg::TW, TH = Cfg::TH;
   constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK;
@@ -96,7 +96,11 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
 
 #pragma unroll 1
     for (int n = 0; n < N; ++n) {
-      // ---- prefetch the next stage (next filter of this item, or the first of the next item)
+      // One barrier per stage: after it, this stage's tile has landed for every thread AND every
+      // warp has finished the previous stage, so the other buffer is free for the next prefetch
+      // (next filter of this item, or the first filter of the next item).
+      cp_async_wait<0>();
+      __syncthreads();
       if (n + 1 < N) {
         stage_g(img0, ty, tx, n + 1, gb ^ 1);
       } else if (item + (int)gridDim.x < p.n_items) {
@@ -104,16 +108,15 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
         stage_g(p.g + (size_t)(nb_ * C + nc_) * N * plane, nty, ntx, 0, gb ^ 1);
       }
       cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
 
       const T *gs = gbuf + gb * TILE + lrow * PITCH + lcol;
 
       // ---- B1: data gradient (correlation of g_n with the flipped filter)
       {
-        const T *wn = cw + n * KK; // this filter's taps; flipped index below = transposed correlation
+        const T *wn0 = cw + n * KK; // this filter's taps; flipped index below = transposed correlation
 #pragma unroll
         for (int rho = 0; rho < RW + K - 1; ++rho) {
+          const T *wn = wn0 + p.zz[rho];
           T row[NV * VEC];
 #pragma unroll
           for (int v = 0; v < NV; ++v)
@@ -132,7 +135,6 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 1) adjoint_k
         }
       }
 
-      __syncthreads(); // stage buffer gb is free again
       gb ^= 1;
     }
 
@@ -244,7 +246,9 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
   cp_async_commit();
 
   for (; item < p.n_items; item += gridDim.x) {
-    // every cp.async group issued so far (this item's u tile, issued one item ago) has landed
+    // One barrier per item: every cp.async group issued so far (this item's u tile, issued one item
+    // ago) has landed, and every warp has finished the previous item, so the other u buffer is
+    // free for the next prefetch.
     cp_async_wait<0>();
     __syncthreads();
 
@@ -317,7 +321,6 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
         }
       }
     }
-    __syncthreads(); // the u tile in `ub` is free again
     ub ^= 1;
   }
   cp_async_wait<0>();

@@ -289,7 +289,8 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
   p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  const int grid = p.n_items < sms ? p.n_items : sms;
+  const int cap = sms * 2; // two resident CTAs per SM
+  const int grid = p.n_items < cap ? p.n_items : cap;
   ProfScope ps(2, st);
   return launch_adjoint<T, K>(p, grid, st);
 }

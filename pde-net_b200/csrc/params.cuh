@@ -46,6 +46,9 @@ template <typename T> struct AdjParams {
   T *lam_out; // [B][C][lo_rows][W]; NULL = skip the data gradient
   int lo_rows, lo_off;
   int slot;           // constant-memory slot holding the N filters [N][K][K]
+  int zz[32];         // all zero; an offset the compiler cannot see through (one per window row), so the
+                      // taps are re-fetched per row into uniform registers instead of being kept
+                      // live in 98 vector registers
   int vec_ok;         // 1: g may be staged in 16-byte units (W % VEC == 0, base 16-byte aligned)
   int B, C, N, H, W;
   int tiles_x, tiles_y, n_items;

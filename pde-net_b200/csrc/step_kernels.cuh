@@ -546,11 +546,13 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   }
 
   for (; item < p.n_items; item += gridDim.x) {
+    // One barrier per item: this item's tile has landed for every thread and every warp has
+    // finished the previous item, so the other buffer can take the next prefetch.
+    cp_async_wait<0>();
+    __syncthreads();
     const int next = item + gridDim.x;
     if (next < p.n_items) stage(next, buf ^ 1);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
 
     const int tx = item % p.tiles_x, t2 = item / p.tiles_x, ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
     const T *tile = tiles + buf * Cfg::TILE_ELEMS;
@@ -671,7 +673,6 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
         }
       }
     }
-    __syncthreads(); // every warp is done with `buf` before the next iteration refills it
     buf ^= 1;
   }
   cp_async_wait<0>();
