@@ -422,7 +422,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
     if (rc) return rc;
     const int n = N * kk;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -567,13 +567,13 @@ static int slab_bwd_end(void *workspace, size_t ws_bytes, T *grad_kernels, T *gr
   if (grad_kernels) {
     const int n = N * k * k;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>((double *)(ws + lay.off_dk), lay.dk_slots, N, k * k, lay.vlb,
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>((double *)(ws + lay.off_dk), lay.dk_slots, N, k * k, lay.vlb,
                                                          grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * symnet_param_count(C * N, L);
     ProfScope ps(4, st);
-    reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>((double *)(ws + lay.off_sym), lay.sym_slots, n, grad_symnet);
+    reduce_flat_kernel<T><<<reduce_blocks(n), 128, 0, st>>>((double *)(ws + lay.off_sym), lay.sym_slots, n, grad_symnet);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -701,12 +701,12 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
   if (grad_kernels) {
     const int n = N * k * k;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * Psym;
     ProfScope ps(4, st);
-    reduce_flat_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(symp, lay.sym_slots, n, grad_symnet);
+    reduce_flat_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(symp, lay.sym_slots, n, grad_symnet);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -854,13 +854,13 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   const int kk = k * k;
   if (grad_id_kernel) {
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<(kk + 127) / 128, 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
+    reduce_dk_kernel<T><<<reduce_blocks(kk), 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
   }
   if (grad_kernels) {
     // filters 1..N: same partial layout, shifted by one filter
     const int n = N * kk;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
                                                          grad_kernels);
   }
   if (grad_coe) {

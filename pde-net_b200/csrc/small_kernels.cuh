@@ -4,24 +4,37 @@
 
 namespace pdenet {
 
-// ---- tiny deterministic finishing kernels ----------------------------------------------------
-// out[n*KK + e] = sum over slots of partial[slot][n][e]   (fixed order)
+// ---- deterministic finishing reductions --------------------------------------------------------
+// One warp per output element: lane l adds slots l, l+32, ... in order, then a fixed shuffle tree.
+// (The first version used one thread per output looping over all ~1800 slots: 0.2 ms of pure
+// latency, half of a config-1 pass.)
+__device__ __forceinline__ double warp_sum_fixed(double s) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  return s;
+}
+
+// out[n*KK + e] = sum over slots of partial[slot][n][e]
 template <typename T>
 __global__ void reduce_dk_kernel(const double *partial, int n_slots, int N, int KK, int VLB, T *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * KK) return;
   const int n = i / KK, e = i % KK;
   double s = 0.0;
-  for (int sl = 0; sl < n_slots; ++sl) s += partial[((size_t)sl * N + n) * VLB + e];
-  out[i] = (T)s;
+  for (int sl = lane; sl < n_slots; sl += 32) s += partial[((size_t)sl * N + n) * VLB + e];
+  s = warp_sum_fixed(s);
+  if (lane == 0) out[i] = (T)s;
 }
 // out[i] = sum over slots of partial[slot][i]
 template <typename T> __global__ void reduce_flat_kernel(const double *partial, int n_slots, int n, T *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n) return;
   double s = 0.0;
-  for (int sl = 0; sl < n_slots; ++sl) s += partial[(size_t)sl * n + i];
-  out[i] = (T)s;
+  for (int sl = lane; sl < n_slots; sl += 32) s += partial[(size_t)sl * n + i];
+  s = warp_sum_fixed(s);
+  if (lane == 0) out[i] = (T)s;
 }
+// launch geometry for the two kernels above: 4 outputs (warps) per 128-thread block
+inline unsigned reduce_blocks(int n_out) { return (unsigned)((n_out + 3) / 4); }
 
 } // namespace pdenet

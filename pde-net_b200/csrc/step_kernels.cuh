@@ -640,36 +640,68 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
           reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
         }
       } else if constexpr (MODE == MODE_LIN_FWD) {
-        // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1
-        const T *coe = p.symnet;
+        // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1.  Loads of the
+        // coefficient fields are issued for the whole strip before use (running pointers).
+        const size_t plane = (size_t)H * W;
+        const T *cp = p.symnet + (size_t)y0 * W + x;
+        T acc[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-          if (valid[j]) {
-            const size_t pix = (size_t)(y0 + j) * W + x;
-            T s = T(0);
+        for (int j = 0; j < P; ++j) acc[j] = T(0);
 #pragma unroll
-            for (int n = 1; n < N; ++n) s = fma_(coe[(size_t)(n - 1) * H * W + pix], d[n][j], s);
-            p.out[((size_t)b * p.out_rows + (y0 + j + p.out_off)) * W + x] = fma_(p.dt, s, d[0][j]);
-          }
+        for (int n = 1; n < N; ++n) {
+#pragma unroll
+          for (int j = 0; j < P; ++j) acc[j] = fma_(cp[(size_t)(valid[j] ? j : 0) * W], d[n][j], acc[j]);
+          cp += plane;
         }
+        T *op = p.out + ((size_t)b * p.out_rows + (y0 + p.out_off)) * W + x;
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          if (valid[j]) op[(size_t)j * W] = fma_(p.dt, acc[j], d[0][j]);
       } else if constexpr (MODE == MODE_LIN_BWD_A) {
         // g_0 = lam, g_n = dt*coe_n*lam;  dcoe_n(y,x) += dt*lam*d_n  (per trajectory, summed later)
-        const T *coe = p.symnet;
+        const size_t plane = (size_t)H * W, gplane = (size_t)p.g_rows * W;
+        const T *lp = p.lam + ((size_t)b * p.lam_rows + (y0 + p.lam_off)) * W + x;
+        T lam[P], lamdt[P];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-          if (valid[j]) {
-            const size_t pix = (size_t)(y0 + j) * W + x;
-            const T lam = p.lam[((size_t)b * p.lam_rows + (y0 + j + p.lam_off)) * W + x];
-            const T lamdt = p.dt * lam;
-            p.g[((size_t)(b * N + 0) * p.g_rows + (y0 + j + p.g_off)) * W + x] = lam;
+          lam[j] = valid[j] ? lp[(size_t)j * W] : T(0);
+          lamdt[j] = p.dt * lam[j];
+        }
+        T *gp = p.g + ((size_t)b * N * p.g_rows + (y0 + p.g_off)) * W + x;
 #pragma unroll
-            for (int n = 1; n < N; ++n) {
-              p.g[((size_t)(b * N + n) * p.g_rows + (y0 + j + p.g_off)) * W + x] =
-                  lamdt * coe[(size_t)(n - 1) * H * W + pix];
-              T *dc = p.dcoe_partial + ((size_t)(b * (N - 1) + (n - 1)) * H) * W + pix;
-              *dc = fma_(lamdt, d[n][j], *dc);
+        for (int j = 0; j < P; ++j)
+          if (valid[j]) gp[(size_t)j * W] = lam[j];
+        const T *cp = p.symnet + (size_t)y0 * W + x;
+        T *dc = p.dcoe_partial + (size_t)b * (N - 1) * plane + (size_t)y0 * W + x;
+        // batches of 4 filters: all loads of a batch are issued before its stores (the compiler
+        // cannot move loads across the stores itself -- the pointers may alias)
+        constexpr int NB = 4;
+#pragma unroll
+        for (int n0 = 1; n0 < N; n0 += NB) {
+          T cv[NB][P], dv[NB][P];
+#pragma unroll
+          for (int q = 0; q < NB; ++q)
+            if (n0 + q < N) {
+#pragma unroll
+              for (int j = 0; j < P; ++j) {
+                const size_t o = (size_t)q * plane + (size_t)(valid[j] ? j : 0) * W;
+                cv[q][j] = cp[o];
+                dv[q][j] = dc[o];
+              }
             }
-          }
+#pragma unroll
+          for (int q = 0; q < NB; ++q)
+            if (n0 + q < N) {
+              gp += gplane;
+#pragma unroll
+              for (int j = 0; j < P; ++j)
+                if (valid[j]) {
+                  gp[(size_t)j * W] = lamdt[j] * cv[q][j];
+                  dc[(size_t)q * plane + (size_t)j * W] = fma_(lamdt[j], d[n0 + q][j], dv[q][j]);
+                }
+            }
+          cp += (size_t)NB * plane;
+          dc += (size_t)NB * plane;
         }
       }
     }

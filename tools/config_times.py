@@ -14,7 +14,11 @@ from bench import model_params, synth_fields
 dev = torch.device("cuda:0")
 
 
+KERNEL_MS = {}
+
+
 def time_it(fn, reps=20):
+    from pdenet_b200 import ops
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -24,7 +28,17 @@ def time_it(fn, reps=20):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    ms = e0.elapsed_time(e1) / reps
+    # second pass with per-launch events: how much of the wall time is inside our kernels
+    ops.profile_read()
+    ops.profile_enable(True)
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    kms, kn = ops.profile_read()
+    ops.profile_enable(False)
+    KERNEL_MS["last"] = ({k: round(v / reps, 4) for k, v in kms.items()}, {k: v // reps for k, v in kn.items()})
+    return ms
 
 
 def symnet_cfg(name, B, H, W, steps, dtype=torch.float64, k=7, C=2, L=2):
@@ -41,7 +55,8 @@ def symnet_cfg(name, B, H, W, steps, dtype=torch.float64, k=7, C=2, L=2):
         out.square().mean().backward()
 
     ms = time_it(fn)
-    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3)}
+    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+            "kernel_ms": KERNEL_MS["last"][0], "launches": KERNEL_MS["last"][1]}
 
 
 def linear_cfg(name, B, H, W, steps, k=5, max_order=4):
@@ -67,7 +82,8 @@ def linear_cfg(name, B, H, W, steps, k=5, max_order=4):
         out.square().mean().backward()
 
     ms = time_it(fn)
-    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3)}
+    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+            "kernel_ms": KERNEL_MS["last"][0], "launches": KERNEL_MS["last"][1]}
 
 
 if __name__ == "__main__":
