@@ -257,9 +257,19 @@ def run_ours(args):
         # one flat all-reduce of every gradient + the loss (no-op at world == 1)
         return parallel.allreduce_gradients(params, loss=loss.detach())
 
+    e2e_chunk = min(Bl, args.e2e_chunk)
+    e2e_bufs = [stage[:e2e_chunk], torch.empty_like(stage[:e2e_chunk])]
+    copy_stream = torch.cuda.Stream(dev)
+
     def one_pass_e2e():
-        stage.copy_(host_u0, non_blocking=True)          # H2D of this pass's inputs (pinned)
-        total = one_pass(stage)
+        # H2D of this pass's inputs from pinned host memory, streamed in chunks of trajectories so
+        # the copy of chunk k+1 overlaps the fwd+bwd rollout of chunk k (parallel.streamed_fwd_bwd)
+        for p in params:
+            p.grad = None
+        loss = parallel.streamed_fwd_bwd(model, host_u0, blocks * dt, 1.0 / (u0[0].numel() * B), e2e_chunk,
+                                         bufs=e2e_bufs, copy_stream=copy_stream)
+        model.diff_grad_proj()
+        total = parallel.allreduce_gradients(params, loss=loss)
         o = 0
         for p in params:                                  # D2H of the gradients + loss
             host_out[o:o + p.numel()].copy_(p.grad.reshape(-1), non_blocking=True)
@@ -352,7 +362,9 @@ def run_ours(args):
                    "parallelism": "dp%d (batch-sharded, one NCCL all-reduce of %d grad scalars)" % (world, nparam + 1),
                    "l2": "inputs (%.1f GB per pass) larger than L2; no flush needed" % (u0.numel() * 8 / 1e9)},
         "e2e": {"value": e2e, "unit": "grid-point-steps/s", "h2d_bytes_per_step": u0.numel() * u0.element_size(),
-                "d2h_bytes_per_step": (nparam + 1) * 8, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": (nparam + 1) * 8, "ms_per_step": ms_e2e / args.steps,
+                "how": "pinned host batch streamed in chunks of %d trajectories; H2D of chunk k+1 overlaps "
+                       "fwd+bwd of chunk k; loss+gradients copied back to pinned host memory" % e2e_chunk},
         "gpu_launches": int(sum(kind_n.values())),
         "clocks": clocks,
         "roofline": {
@@ -386,6 +398,7 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override the grid side (debug only)")
     ap.add_argument("--blocks", type=int, default=0, help="override the number of dt-blocks (debug only)")
     ap.add_argument("--chunk", type=int, default=16, help="trajectories per reverse-kernel launch")
+    ap.add_argument("--e2e-chunk", type=int, default=32, help="trajectories per streamed chunk of the e2e pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

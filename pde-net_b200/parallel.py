@@ -157,3 +157,47 @@ class SlabDecomposition:
         gk, gs = bwd.finish()
         flat_allreduce([gk, gs], group=self.group)
         return final, lam, gk, gs
+
+
+def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, chunk: int,
+                     bufs=None, copy_stream=None):
+    """End-to-end pass over a batch that lives in PINNED HOST memory: trajectories are independent,
+    so the batch is streamed through the device in chunks -- the host-to-device copy of chunk k+1
+    (on a side stream) overlaps the fused forward + reverse rollout of chunk k, and the parameter
+    gradients accumulate in ``.grad``.  Loss = ``loss_scale * sum(final_state**2)`` summed over
+    chunks (``loss_scale = 1/numel`` gives the mean square).  Returns the summed loss (0-dim
+    device tensor)."""
+    dev = next(model.parameters()).device
+    B = host_u0.shape[0]
+    main = torch.cuda.current_stream(dev)
+    copy_stream = copy_stream or torch.cuda.Stream(dev)
+    if bufs is None:
+        bufs = [torch.empty((min(chunk, B),) + tuple(host_u0.shape[1:]), dtype=host_u0.dtype, device=dev)
+                for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    total = torch.zeros((), dtype=host_u0.dtype, device=dev)
+    starts = list(range(0, B, chunk))
+
+    def issue_copy(k):
+        b0 = starts[k]
+        nb = min(chunk, B - b0)
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(freed[k % 2])     # chunk k-2 has finished with this buffer
+            bufs[k % 2][:nb].copy_(host_u0[b0:b0 + nb], non_blocking=True)
+            copied[k % 2].record(copy_stream)
+        return nb
+
+    copy_stream.wait_stream(main)
+    nbs = {0: issue_copy(0)}
+    for k in range(len(starts)):
+        if k + 1 < len(starts):
+            nbs[k + 1] = issue_copy(k + 1)
+        main.wait_event(copied[k % 2])
+        out = model(bufs[k % 2][:nbs[k]], T)
+        loss = out.square().sum() * loss_scale
+        loss.backward()
+        total = total + loss.detach()
+        freed[k % 2].record(main)
+    return total

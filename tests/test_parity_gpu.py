@@ -390,6 +390,35 @@ def test_slab_bwd_multi_slab_emulated(P, cuda_device):
     assert rel(gs, sd.grad) < 1e-12
 
 
+def test_streamed_fwd_bwd_equals_resident(P, cuda_device):
+    """parallel.streamed_fwd_bwd (pinned host batch, chunked H2D overlapped with compute) gives the
+    same loss and parameter gradients as one resident pass."""
+    from pdenet_b200 import parallel as PP
+    dt, dx, k, L = 1e-3, 0.1, 5, 2
+    model = P.POLYPDE2D(dt, dx, k, 2, "moment", "u,v", hidden_layers=L).to(cuda_device)
+    g = torch.Generator().manual_seed(71)
+    with torch.no_grad():
+        for fd in model.fds:
+            fd.moment.add_((1e-2 * torch.randn(k, k, generator=g, dtype=torch.float64)).to(cuda_device))
+        model.diff_x_proj()
+        for p in model.expr_params():
+            p.copy_((0.1 * torch.randn(p.shape, generator=g, dtype=torch.float64)).to(cuda_device))
+    u0 = smooth_field(7, 2, 24, 20, 72)
+    host = u0.pin_memory()
+    scale = 1.0 / u0.numel()
+    out = model(u0.to(cuda_device), 3 * dt)
+    ref_loss = out.square().sum() * scale
+    ref_loss.backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    for p in model.parameters():
+        p.grad = None
+    loss = PP.streamed_fwd_bwd(model, host, 3 * dt, scale, chunk=3)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss.item()) < 1e-12 * abs(ref_loss.item())
+    for p, r in zip(model.parameters(), ref):
+        assert rel(p.grad, r) < 1e-11
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib
