@@ -217,7 +217,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.float64
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
     B, C, H, W, k, L, blocks = (args.batch or CFG["B"]), CFG["C"], args.size or CFG["H"], args.size or CFG["W"], \
         CFG["k"], CFG["L"], args.blocks or CFG["blocks"]
     assert B % world == 0, "global batch must divide over the ranks"
@@ -226,7 +226,8 @@ def run_ours(args):
     dt = 0.25 * dx * dx
     chunk = min(Bl, args.chunk)
 
-    model = P.POLYPDE2D(dt, dx, k, CFG["max_order"], "moment", "u,v", hidden_layers=L, batch_chunk=chunk).to(dev)
+    model = P.POLYPDE2D(dt, dx, k, CFG["max_order"], "moment", "u,v", hidden_layers=L, batch_chunk=chunk,
+                        dtype=dtype).to(dev)
     orders, M, scales, sym = model_params(k, CFG["max_order"], C, L, dx)
     with torch.no_grad():
         for fd, m in zip(model.fds, M):
@@ -356,8 +357,9 @@ def run_ours(args):
     line = {
         "metric": "grid-point-steps/sec fwd+bwd rollout", "value": value, "unit": "grid-point-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": CFG["workload"], "global_batch": B, "per_gpu_batch": Bl, "grid": [H, W],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": CFG["workload"] if args.dtype == "f64" else CFG["workload"].replace("fp64", "fp32"),
+                   "global_batch": B, "per_gpu_batch": Bl, "grid": [H, W],
                    "dt_blocks": blocks, "max_order": CFG["max_order"], "dt": dt, "batch_chunk": chunk,
                    "parallelism": "dp%d (batch-sharded, one NCCL all-reduce of %d grad scalars)" % (world, nparam + 1),
                    "l2": "inputs (%.1f GB per pass) larger than L2; no flush needed" % (u0.numel() * 8 / 1e9)},
@@ -368,7 +370,7 @@ def run_ours(args):
         "gpu_launches": int(sum(kind_n.values())),
         "clocks": clocks,
         "roofline": {
-            "bound": "fp64", "kernel": KERNEL_NAMES[top],
+            "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": KERNEL_NAMES[top].replace("double", "double" if args.dtype == "f64" else "float"),
             "achieved": achieved, "peak": fma_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fma_peak / 1e12),
             "peak_source": "measured this run: pdenet_fma_peak register-only DFMA loop (nominal %.0f)" % NOMINAL_FP64_TFLOPS,
             "flops_per_launch": KERNEL_FLOPS[top] * pts_per_launch, "ms_per_launch": ms_top, "launches": n_top,
@@ -400,6 +402,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=16, help="trajectories per reverse-kernel launch")
     ap.add_argument("--e2e-chunk", type=int, default=32, help="trajectories per streamed chunk of the e2e pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f64 = the reference's precision (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,7 +23,10 @@ template <typename T> struct TransposeCfg {
 template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = NT_;
-  static constexpr int P = 4;
+  // points per thread strip: 4 in fp64; 8 in fp32 (FFMA issues every cycle, so each uniform tap
+  // load has to feed twice as many FMAs to stay off the issue-slot limit) when the C*N features of
+  // 8 points still fit the register file
+  static constexpr int P = (sizeof(T) == 4 && C * N <= 12) ? 8 : 4;
   static constexpr int TW = 64, TH = (NT / 64) * 2 * P; // 2 warps across, NT/64 down, 2 strips of P rows each
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH = SC;
@@ -638,6 +641,10 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
         } else {
           reverse_half<T, M, P, 0, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
           reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+          if constexpr (P == 8) {
+            reverse_half<T, M, P, 4, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+            reverse_half<T, M, P, 6, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+          }
         }
       } else if constexpr (MODE == MODE_LIN_FWD) {
         // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1.  Loads of the
