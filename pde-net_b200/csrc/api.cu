@@ -85,11 +85,16 @@ struct SlotLease {
     }
     slot = g_slots.next;
     g_slots.next = (g_slots.next + 1) % kConstSlots;
-    cudaStreamWaitEvent(st, g_slots.ev[dev][slot], 0);
+    // inside a CUDA-graph capture the guard events cannot be used (they were recorded outside the
+    // capture); the captured work is stream-ordered within the graph, which is all it needs
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (!capturing) cudaStreamWaitEvent(st, g_slots.ev[dev][slot], 0);
   }
   ~SlotLease() {
-    if (slot >= 0) cudaEventRecord(g_slots.ev[dev][slot], st);
+    if (slot >= 0 && !capturing) cudaEventRecord(g_slots.ev[dev][slot], st);
   }
+  bool capturing = false;
 };
 
 #define PDENET_DISPATCH_K(k, EXPR)                                                                                \

@@ -419,6 +419,43 @@ def test_streamed_fwd_bwd_equals_resident(P, cuda_device):
         assert rel(p.grad, r) < 1e-11
 
 
+def test_cuda_graph_capture_small_config(P, cuda_device):
+    """Small configs are launch-bound: the whole fwd+bwd (m2k, rollout, loss, reverse) captures
+    into one CUDA graph and replays bit-identically (BASELINE config 1 shape)."""
+    k, max_order, C, L, B, H, W, steps, dx, dt = CASES[0]
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 81)
+    scales = scales.tolist()
+    Md = M.to(cuda_device).requires_grad_(True)
+    sd = sym.to(cuda_device).requires_grad_(True)
+    u = smooth_field(B, C, H, W, 82).to(cuda_device)
+
+    def fwd_bwd():
+        Md.grad = None
+        sd.grad = None
+        out = P.rollout(u, P.m2k(Md, scales), sd, L, dt, steps, last_only=True)
+        out.square().mean().backward()
+        return out
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            ref = fwd_bwd()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    ref_out, ref_gm, ref_gs = ref.detach().clone(), Md.grad.clone(), sd.grad.clone()
+    Md.grad = torch.zeros_like(Md)
+    sd.grad = torch.zeros_like(sd)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = P.rollout(u, P.m2k(Md, scales), sd, L, dt, steps, last_only=True)
+        gm, gs = torch.autograd.grad(out.square().mean(), (Md, sd))
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out) and torch.equal(gm, ref_gm) and torch.equal(gs, ref_gs)
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib

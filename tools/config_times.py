@@ -17,6 +17,29 @@ dev = torch.device("cuda:0")
 KERNEL_MS = {}
 
 
+def time_graph(fn_graphable, reps=50):
+    """Capture one fwd+bwd into a CUDA graph and time the replays (launch overhead removed)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn_graphable()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn_graphable()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def time_it(fn, reps=20):
     from pdenet_b200 import ops
     for _ in range(3):
@@ -55,7 +78,15 @@ def symnet_cfg(name, B, H, W, steps, dtype=torch.float64, k=7, C=2, L=2):
         out.square().mean().backward()
 
     ms = time_it(fn)
-    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+
+    def fng():
+        out = P.rollout(u0, P.m2k(M, scales), sym, L, dt, steps, last_only=True)
+        return torch.autograd.grad(out.square().mean(), (M, sym))
+
+    msg = time_graph(fng)
+    return {"config": name, "ms_fwd_bwd": ms, "ms_fwd_bwd_cuda_graph": msg,
+            "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+            "grid_point_steps_per_s_cuda_graph": B * H * W * steps / (msg * 1e-3),
             "kernel_ms": KERNEL_MS["last"][0], "launches": KERNEL_MS["last"][1]}
 
 
@@ -82,7 +113,16 @@ def linear_cfg(name, B, H, W, steps, k=5, max_order=4):
         out.square().mean().backward()
 
     ms = time_it(fn)
-    return {"config": name, "ms_fwd_bwd": ms, "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+
+    def fng():
+        ks = P.m2k(M, scales)
+        out = P.linear_rollout(u0, ks[0], ks[1:], coe, dt, steps, last_only=True)
+        return torch.autograd.grad(out.square().mean(), (M, coe))
+
+    msg = time_graph(fng)
+    return {"config": name, "ms_fwd_bwd": ms, "ms_fwd_bwd_cuda_graph": msg,
+            "grid_point_steps_per_s": B * H * W * steps / (ms * 1e-3),
+            "grid_point_steps_per_s_cuda_graph": B * H * W * steps / (msg * 1e-3),
             "kernel_ms": KERNEL_MS["last"][0], "launches": KERNEL_MS["last"][1]}
 
 
