@@ -129,34 +129,37 @@ class SlabDecomposition:
         a sum over ranks of local terms).  Returns ``(final_local, grad_u0_local, grad_kernels,
         grad_symnet)`` with the parameter gradients already summed over the ranks (one flat
         all-reduce).  ``bwd_factory(kernels, symnet, L, dt, B, C, Hs, W)`` defaults to the CUDA
-        ``ops.SlabBackward``."""
+        ``ops.SlabBackward``.
+
+        No full-slab copies: every forward state lives in its own buffer with 2r ghost rows (the
+        forward exchanges 2r rows, so the reverse pass needs no state exchange at all), each step
+        writes straight into the interior of the next buffer, and the reverse step writes the new
+        adjoint into the interior of the next r-ghosted adjoint buffer."""
         from . import ops
         if step_fn is None:
             step_fn = ops.slab_step
         if bwd_factory is None:
             bwd_factory = ops.SlabBackward
         h = self.halo
+        h2 = 2 * h
         B, C, Hs, W = u_local.shape
-        states = [u_local]                       # owned rows of u_0 .. u_steps
-        a = self.extend(u_local)
+        bufs = [self.extend(u_local, h2)]            # u_0 .. u_steps, each with 2r ghost rows
         for _ in range(steps):
-            self.exchange(a)
-            nxt = torch.empty_like(a)
-            step_fn(a, kernels, symnet, L, dt, h, nxt, h)
-            states.append(nxt[:, :, h:h + Hs].contiguous())
-            a = nxt
-        final = states[-1]
-        lam = grad_last_local(final).contiguous()
+            self.exchange(bufs[-1], h2)
+            nxt = torch.empty_like(bufs[-1])
+            step_fn(bufs[-1], kernels, symnet, L, dt, h2, nxt, h2)
+            bufs.append(nxt)
+        final = bufs[-1][:, :, h2:h2 + Hs].contiguous()
+        lam_ext = self.extend(grad_last_local(final).contiguous(), h)
+        lam_nxt = torch.empty_like(lam_ext)
         bwd = bwd_factory(kernels, symnet, L, dt, B, C, Hs, W)
         for t in range(steps - 1, -1, -1):
-            u2 = self.extend(states[t], 2 * h)
-            self.exchange(u2, 2 * h)
-            lam_ext = self.extend(lam, h)
             self.exchange(lam_ext, h)
-            lam = bwd.step(u2, lam_ext, torch.empty_like(lam))
+            bwd.step(bufs[t], lam_ext, lam_nxt, h)   # bufs[t] already carries its 2r ghost rows
+            lam_ext, lam_nxt = lam_nxt, lam_ext
         gk, gs = bwd.finish()
         flat_allreduce([gk, gs], group=self.group)
-        return final, lam, gk, gs
+        return final, lam_ext[:, :, h:h + Hs].contiguous(), gk, gs
 
 
 def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, chunk: int,
