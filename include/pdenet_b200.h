@@ -148,6 +148,20 @@ PDENET_API int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels
                              int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
                              int N, int L, double dt, void *stream);
 
+/* Same forward slab step with the halo exchange fused in: besides its own rows the kernel stores
+ * its first / last `mirror_rows` output rows straight into the ring neighbours' output buffers
+ * (peer_up_out / peer_down_out: device pointers to the neighbours' buffers of the SAME layout,
+ * mapped into this process -- CUDA IPC / symmetric memory over NVLink), where they are the
+ * neighbours' bottom / top ghost rows.  The caller synchronises the ranks between steps. */
+PDENET_API int pdenet_slab_step_fwd_p2p_f64(const double *u_ext, const double *kernels, const double *symnet, double *out,
+                                 double *peer_up_out, double *peer_down_out, int mirror_rows, int B, int C, int Hs,
+                                 int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
+                                 double dt, void *stream);
+PDENET_API int pdenet_slab_step_fwd_p2p_f32(const float *u_ext, const float *kernels, const float *symnet, float *out,
+                                 float *peer_up_out, float *peer_down_out, int mirror_rows, int B, int C, int Hs,
+                                 int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
+                                 double dt, void *stream);
+
 /* Reverse of one slab step.  u_ext: state at the step's input, [B,C,Hs+4r,W] with 2r ghost rows
  * on each side (r = (k-1)/2); lam_ext: adjoint of the step's output INCLUDING this step's loss
  * seed, [B,C,Hs+2r,W] with r ghost rows on each side.  Writes the adjoint of the step's input for
@@ -166,6 +180,17 @@ PDENET_API int pdenet_slab_step_bwd_f32(const float *u_ext, const float *lam_ext
                              const float *symnet, float *lam_out, int out_rows_per_image, int out_row_offset,
                              void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
                              int L, double dt, void *stream);
+/* pdenet_slab_step_bwd with the adjoint halo exchange fused in (see pdenet_slab_step_fwd_p2p). */
+PDENET_API int pdenet_slab_step_bwd_p2p_f64(const double *u_ext, const double *lam_ext, const double *kernels,
+                                 const double *symnet, double *lam_out, double *peer_up_out, double *peer_down_out,
+                                 int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                 size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                 void *stream);
+PDENET_API int pdenet_slab_step_bwd_p2p_f32(const float *u_ext, const float *lam_ext, const float *kernels,
+                                 const float *symnet, float *lam_out, float *peer_up_out, float *peer_down_out,
+                                 int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                 size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                 void *stream);
 PDENET_API int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *grad_kernels, double *grad_symnet,
                             int B, int C, int Hs, int W, int k, int N, int L, void *stream);
 PDENET_API int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet,

@@ -173,7 +173,15 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
           const int y = y0 + j0 + jj;
 #pragma unroll
           for (int i = 0; i < VEC; ++i)
-            if (y < H && okx[i]) lo[(size_t)y * W + xx[i]] = lacc[j0 + jj][i] + add[jj][i];
+            if (y < H && okx[i]) {
+              const T v = lacc[j0 + jj][i] + add[jj][i];
+              lo[(size_t)y * W + xx[i]] = v;
+              if (p.mirror_rows) { // fused adjoint halo exchange: peer stores over NVLink
+                const size_t rb = img * p.lo_rows + p.lo_off;
+                if (y < p.mirror_rows) p.peer_up[(rb + H + y) * W + xx[i]] = v;
+                if (y >= H - p.mirror_rows) p.peer_dn[(rb + y - H) * W + xx[i]] = v;
+              }
+            }
         }
       }
     }

@@ -433,8 +433,12 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
 }
 
 template <typename T>
-static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *out, int B, int C, int Hs, int W,
-                         int halo, int out_rows, int out_off, int k, int N, int L, double dt, void *stream) {
+static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *out, T *peer_up, T *peer_dn,
+                         int mirror_rows, int B, int C, int Hs, int W, int halo, int out_rows, int out_off, int k,
+                         int N, int L, double dt, void *stream) {
+  if (mirror_rows < 0 || mirror_rows > Hs || mirror_rows > out_off || (mirror_rows > 0 && (!peer_up || !peer_dn)) ||
+      out_rows < Hs + out_off + mirror_rows)
+    return PDENET_E_BADARG;
   if (!u_ext || !kernels || !symnet || !out || bad_geom(B, C, Hs, W, k, N) || L < 0 || halo < (k - 1) / 2 ||
       out_rows < Hs + out_off || out_off < 0)
     return PDENET_E_BADARG;
@@ -455,6 +459,9 @@ static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *o
   p.out = out;
   p.out_rows = out_rows;
   p.out_off = out_off;
+  p.peer_up = peer_up;
+  p.peer_dn = peer_dn;
+  p.mirror_rows = mirror_rows;
   int rc = 0;
   PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, Hs, W, (cudaStream_t)stream)));
   return rc;
@@ -483,9 +490,12 @@ static SlabLayout slab_layout(size_t es, int B, int C, int Hs, int W, int k, int
 }
 
 template <typename T>
-static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, const T *symnet, T *lam_out,
-                         int out_rows, int out_off, void *workspace, size_t ws_bytes, int B, int C, int Hs, int W,
-                         int k, int N, int L, double dt, void *stream) {
+static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, const T *symnet, T *lam_out, T *peer_up,
+                         T *peer_dn, int mirror_rows, int out_rows, int out_off, void *workspace, size_t ws_bytes,
+                         int B, int C, int Hs, int W, int k, int N, int L, double dt, void *stream) {
+  if (mirror_rows < 0 || mirror_rows > Hs || mirror_rows > out_off || (mirror_rows > 0 && (!peer_up || !peer_dn)) ||
+      out_rows < Hs + out_off + mirror_rows)
+    return PDENET_E_BADARG;
   if (!u_ext || !lam_ext || !kernels || !symnet || !lam_out || !workspace || bad_geom(B, C, Hs, W, k, N) || L < 0 ||
       out_off < 0 || out_rows < Hs + out_off)
     return PDENET_E_BADARG;
@@ -541,6 +551,9 @@ static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, con
   q.lam_out = lam_out;
   q.lo_rows = out_rows;
   q.lo_off = out_off;
+  q.peer_up = peer_up;
+  q.peer_dn = peer_dn;
+  q.mirror_rows = mirror_rows;
   q.slot = lease.slot;
   int rc = 0;
   PDENET_DISPATCH_K(k, rc = (run_adjoint<T, KK_>(q, B, C, N, Hs, W, st)));
@@ -1075,14 +1088,14 @@ int pdenet_linear_rollout_bwd_f32(const float *u0, const float *states, const fl
 int pdenet_slab_step_fwd_f64(const double *u_ext, const double *kernels, const double *symnet, double *out, int B,
                              int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
                              int N, int L, double dt, void *st) {
-  return slab_step_fwd<double>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset,
-                               k, N, L, dt, st);
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, nullptr, nullptr, 0, B, C, Hs, W, halo,
+                               out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const float *symnet, float *out, int B, int C,
                              int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N,
                              int L, double dt, void *st) {
-  return slab_step_fwd<float>(u_ext, kernels, symnet, out, B, C, Hs, W, halo, out_rows_per_image, out_row_offset, k,
-                              N, L, dt, st);
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, nullptr, nullptr, 0, B, C, Hs, W, halo,
+                              out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 
 size_t pdenet_slab_bwd_workspace_bytes(int elem_size, int B, int C, int Hs, int W, int k, int N, int L) {
@@ -1108,15 +1121,47 @@ int pdenet_slab_step_bwd_f64(const double *u_ext, const double *lam_ext, const d
                              const double *symnet, double *lam_out, int out_rows_per_image, int out_row_offset,
                              void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
                              int L, double dt, void *st) {
-  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, out_rows_per_image, out_row_offset,
-                               workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
+  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
+                               out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
 }
 int pdenet_slab_step_bwd_f32(const float *u_ext, const float *lam_ext, const float *kernels, const float *symnet,
                              float *lam_out, int out_rows_per_image, int out_row_offset, void *workspace,
                              size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
                              void *st) {
-  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, out_rows_per_image, out_row_offset, workspace,
-                              workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
+  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
+                              out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
+}
+int pdenet_slab_step_fwd_p2p_f64(const double *u_ext, const double *kernels, const double *symnet, double *out,
+                                 double *peer_up_out, double *peer_down_out, int mirror_rows, int B, int C, int Hs,
+                                 int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
+                                 double dt, void *st) {
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
+                               out_rows_per_image, out_row_offset, k, N, L, dt, st);
+}
+int pdenet_slab_step_fwd_p2p_f32(const float *u_ext, const float *kernels, const float *symnet, float *out,
+                                 float *peer_up_out, float *peer_down_out, int mirror_rows, int B, int C, int Hs,
+                                 int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
+                                 double dt, void *st) {
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
+                              out_rows_per_image, out_row_offset, k, N, L, dt, st);
+}
+int pdenet_slab_step_bwd_p2p_f64(const double *u_ext, const double *lam_ext, const double *kernels,
+                                 const double *symnet, double *lam_out, double *peer_up_out, double *peer_down_out,
+                                 int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                 size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                 void *st) {
+  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+                               out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L,
+                               dt, st);
+}
+int pdenet_slab_step_bwd_p2p_f32(const float *u_ext, const float *lam_ext, const float *kernels,
+                                 const float *symnet, float *lam_out, float *peer_up_out, float *peer_down_out,
+                                 int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                 size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                 void *st) {
+  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+                              out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt,
+                              st);
 }
 int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *grad_kernels, double *grad_symnet, int B,
                             int C, int Hs, int W, int k, int N, int L, void *st) {

@@ -15,6 +15,11 @@ template <typename T> struct StepParams {
   // forward output [B][C][out_rows][W] / features [B][C*N][out_rows][W]
   T *out;
   int out_rows, out_off;
+  // slab mode with peer halo writes (NVLink peer memory): the first / last `mirror_rows` output
+  // rows are also stored into the ring neighbours' output buffers (same layout), where they are
+  // the neighbours' bottom / top ghost rows.  mirror_rows == 0: off.
+  T *peer_up, *peer_dn;
+  int mirror_rows;
   // reverse: adjoint of the step's output [B][C][lam_rows][W]
   const T *lam;
   int lam_rows, lam_off;
@@ -45,6 +50,8 @@ template <typename T> struct AdjParams {
   int inj_rows, inj_off;
   T *lam_out; // [B][C][lo_rows][W]; NULL = skip the data gradient
   int lo_rows, lo_off;
+  T *peer_up, *peer_dn; // slab mode: mirror the first / last mirror_rows rows into the neighbours' lam_out
+  int mirror_rows;
   int slot;           // constant-memory slot holding the N filters [N][K][K]
   int zz[32];         // all zero; an offset the compiler cannot see through (one per window row), so the
                       // taps are re-fetched per row into uniform registers instead of being kept

@@ -625,7 +625,16 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
           T *op = p.out + ((size_t)(b * C + co) * p.out_rows + (y0 + p.out_off)) * W + x;
 #pragma unroll
           for (int j = 0; j < P; ++j)
-            if (valid[j]) op[(size_t)j * W] = fma_(p.dt, fout[j], uc[j * PITCH]);
+            if (valid[j]) {
+              const T v = fma_(p.dt, fout[j], uc[j * PITCH]);
+              op[(size_t)j * W] = v;
+              if (p.mirror_rows) { // fused halo exchange: peer stores over NVLink
+                const int y = y0 + j;
+                const size_t img = (size_t)(b * C + co) * p.out_rows;
+                if (y < p.mirror_rows) p.peer_up[(img + p.out_off + H + y) * W + x] = v;
+                if (y >= H - p.mirror_rows) p.peer_dn[(img + p.out_off + y - H) * W + x] = v;
+              }
+            }
         }
       } else if constexpr (MODE == MODE_BWD_A) {
         // ---- SymNet reverse, two points at a time (register budget), rows a7/a11

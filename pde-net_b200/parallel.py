@@ -162,6 +162,79 @@ class SlabDecomposition:
         return final, lam_ext[:, :, h:h + Hs].contiguous(), gk, gs
 
 
+class SlabPeerBuffers:
+    """State / adjoint buffers of a slab rollout in SYMMETRIC memory (every rank allocates the same
+    layout and maps its ring neighbours' copies over NVLink), so the step kernels can store their
+    boundary rows straight into the neighbours' ghost rows: the halo exchange is fused into the
+    compute kernel instead of being an NCCL send/recv between steps.  One ``barrier()`` (a
+    symmetric-memory signal exchange on the stream) separates consecutive steps."""
+
+    def __init__(self, slab: "SlabDecomposition", B: int, C: int, W: int, steps: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.slab, self.steps = slab, steps
+        h, h2, Hs = slab.halo, 2 * slab.halo, slab.Hs
+        self.n_state = B * C * (Hs + 2 * h2) * W
+        self.n_lam = B * C * (Hs + 2 * h) * W
+        total = (steps + 1) * self.n_state + 2 * self.n_lam
+        self.flat = symm_mem.empty(total, dtype=dtype, device=device)
+        if slab.world > 1:
+            group = slab.group if slab.group is not None else dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.flat, group.group_name)
+            ptrs = self.hdl.buffer_ptrs
+        else:
+            self.hdl, ptrs = None, [self.flat.data_ptr()]
+        es = self.flat.element_size()
+        self.base_up, self.base_dn = ptrs[slab.up], ptrs[slab.down]
+        self.state = [self.flat[i * self.n_state:(i + 1) * self.n_state].view(B, C, Hs + 2 * h2, W)
+                      for i in range(steps + 1)]
+        o = (steps + 1) * self.n_state
+        self.lam = [self.flat[o + i * self.n_lam:o + (i + 1) * self.n_lam].view(B, C, Hs + 2 * h, W) for i in range(2)]
+        self._es, self._lam_off = es, o
+
+    def state_peers(self, i):
+        off = i * self.n_state * self._es
+        return self.base_up + off, self.base_dn + off
+
+    def lam_peers(self, i):
+        off = (self._lam_off + i * self.n_lam) * self._es
+        return self.base_up + off, self.base_dn + off
+
+    def barrier(self):
+        if self.hdl is not None:
+            self.hdl.barrier()
+
+
+def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u_local: torch.Tensor,
+                             kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
+                             grad_last_local: Callable):
+    """``SlabDecomposition.rollout_fwd_bwd`` with the halo exchanges fused into the step kernels
+    (peer stores into the neighbours' ghost rows, `SlabPeerBuffers`).  Only the initial state and
+    the loss seed need a conventional ghost fill."""
+    from . import ops
+    h, h2, Hs = slab.halo, 2 * slab.halo, slab.Hs
+    B, C, _, W = u_local.shape
+    bufs.state[0][:, :, h2:h2 + Hs] = u_local
+    slab.exchange(bufs.state[0], h2)
+    bufs.barrier()                                   # every rank's buffers are ready to be written
+    for t in range(steps):
+        up, dn = bufs.state_peers(t + 1)
+        ops.slab_step(bufs.state[t], kernels, symnet, L, dt, h2, bufs.state[t + 1], h2, up, dn, h2)
+        bufs.barrier()                               # neighbours' boundary rows have landed
+    final = bufs.state[steps][:, :, h2:h2 + Hs].contiguous()
+    cur = 0
+    bufs.lam[cur][:, :, h:h + Hs] = grad_last_local(final)
+    slab.exchange(bufs.lam[cur], h)
+    bwd = ops.SlabBackward(kernels, symnet, L, dt, B, C, Hs, W)
+    for t in range(steps - 1, -1, -1):
+        up, dn = bufs.lam_peers(cur ^ 1)
+        bwd.step(bufs.state[t], bufs.lam[cur], bufs.lam[cur ^ 1], h, up, dn, h)
+        bufs.barrier()
+        cur ^= 1
+    gk, gs = bwd.finish()
+    flat_allreduce([gk, gs], group=slab.group)
+    return final, bufs.lam[cur][:, :, h:h + Hs].contiguous(), gk, gs
+
+
 def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, chunk: int,
                      bufs=None, copy_stream=None):
     """End-to-end pass over a batch that lives in PINNED HOST memory: trajectories are independent,

@@ -361,6 +361,27 @@ def test_slab_fwd_bwd_single_rank_matches_autograd(P, cuda_device, dtype):
     assert rel(gs, sd.grad) < 1e-12
 
 
+def test_slab_p2p_single_rank_matches_autograd(P, cuda_device):
+    """Fused halo writes (peer stores) with the rank as its own neighbour (world 1)."""
+    from pdenet_b200 import parallel as PP
+    k, max_order, C, L, dx, dt, steps = 7, 2, 2, 2, 0.1, 1e-3, 3
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 53)
+    Ks = O.scaled_kernels(M, scales).to(cuda_device)
+    sym = sym.to(cuda_device)
+    u = smooth_field(2, C, 48, 40, 54).to(cuda_device)
+    w = torch.randn(u.shape, generator=torch.Generator().manual_seed(7), dtype=torch.float64).to(cuda_device)
+    ud, Kd, sd = [t.clone().requires_grad_(True) for t in (u, Ks, sym)]
+    ref = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True)
+    (ref * w).sum().backward()
+    slab = PP.SlabDecomposition(48, 3, 0, 1)
+    bufs = PP.SlabPeerBuffers(slab, 2, C, 40, steps, torch.float64, cuda_device)
+    fin, gu, gk, gs = PP.slab_rollout_fwd_bwd_p2p(slab, bufs, u, Ks, sym, L, dt, steps, lambda f: w)
+    assert torch.equal(fin, ref.detach())
+    assert rel(gu, ud.grad) < 1e-12
+    assert rel(gk, Kd.grad) < 1e-12
+    assert rel(gs, sd.grad) < 1e-12
+
+
 def test_slab_bwd_multi_slab_emulated(P, cuda_device):
     """Four slabs of one grid processed one after the other on one GPU (ghost rows gathered by
     indexing instead of NVLink): summed parameter gradients and stitched input gradient equal the

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--p2p", action="store_true", help="fused peer-memory halo writes instead of NCCL send/recv")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -48,7 +49,16 @@ def main():
     def seed(f):  # loss = mean square of the final state over the WHOLE grid
         return 2.0 * f / n_total
 
-    fin, gu, gk, gs = slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, a.steps, seed)
+    if a.p2p:
+        pb = PP.SlabPeerBuffers(slab, 1, C, W, a.steps, dtype, dev)
+
+        def run():
+            return PP.slab_rollout_fwd_bwd_p2p(slab, pb, mine, Ks, sym, L, dt, a.steps, seed)
+    else:
+        def run():
+            return slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, a.steps, seed)
+
+    fin, gu, gk, gs = run()
     torch.cuda.synchronize()
     errs = None
     if not a.no_check:
@@ -68,7 +78,7 @@ def main():
     torch.cuda.synchronize()
     e0.record()
     for _ in range(a.reps):
-        slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, a.steps, seed)
+        run()
     e1.record()
     dist.barrier()
     torch.cuda.synchronize()
@@ -76,7 +86,7 @@ def main():
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         tol = 1e-10 * a.steps if dtype == torch.float64 else 1e-3
-        out = {"what": "slab-decomposed fwd+bwd rollout, 1 trajectory", "n_gpus": world, "grid": [H, W], "dtype": a.dtype,
+        out = {"what": "slab-decomposed fwd+bwd rollout, 1 trajectory" + (", fused peer halo writes" if a.p2p else ", NCCL halo exchange"), "n_gpus": world, "grid": [H, W], "dtype": a.dtype,
                "steps": a.steps, "ms_per_pass": ms.item(), "grid_point_steps_per_s": H * W * a.steps / (ms.item() * 1e-3),
                "max_rel_err_vs_single_gpu": None if errs is None else
                dict(zip(["state", "grad_u0", "grad_kernels", "grad_symnet"], errs.tolist()))}
