@@ -196,6 +196,19 @@ PDENET_API int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, 
 PDENET_API int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet,
                             int B, int C, int Hs, int W, int k, int N, int L, void *stream);
 
+/* ---- training-loss seed fused into one pass (upstream: the MSE data term of the
+ * loss closure in train.py) -------------------------------------------------------------------
+ * loss = sum_t w_t * mean((states[t] - observed[t])^2) over t < steps, each step n_per_step scalars;
+ * grad_states[t] = 2 w_t (states[t] - observed[t]) / n_per_step (the seed pdenet_rollout_bwd takes
+ * with PDENET_GRAD_ALL).  weights_host: `steps` host scalars (NULL = all 1).  loss_out: one device
+ * double.  Deterministic (fixed-order two-stage reduction).  Workspace: 8 KiB. */
+PDENET_API int pdenet_mse_seed_f64(const double *states, const double *observed, const double *weights_host,
+                        double *grad_states, double *loss_out, size_t n_per_step, int steps, void *workspace,
+                        size_t workspace_bytes, void *stream);
+PDENET_API int pdenet_mse_seed_f32(const float *states, const float *observed, const double *weights_host,
+                        float *grad_states, double *loss_out, size_t n_per_step, int steps, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
  * 2 = reverse kernel B1 (data gradient), 3 = reverse kernel B2 (filter gradient),

@@ -42,6 +42,7 @@ _PROTOS = {
     "pdenet_slab_bwd_begin": (_i, [_vp, _sz] + [_i] * 8 + [_vp]),
     "pdenet_slab_step_bwd_{t}": (_i, [_vp] * 5 + [_i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
     "pdenet_slab_bwd_end_{t}": (_i, [_vp, _sz, _vp, _vp] + [_i] * 7 + [_vp]),
+    "pdenet_mse_seed_{t}": (_i, [_vp] * 5 + [_sz, _i, _vp, _sz, _vp]),
     "pdenet_profile_enable": (_i, [_i]),
     "pdenet_profile_read": (_i, [C.POINTER(_d), C.POINTER(C.c_longlong)]),
     "pdenet_fma_peak": (_i, [_i, _i, C.POINTER(_d), C.POINTER(C.c_float), _vp]),

@@ -889,6 +889,26 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
 
+// ---- fused MSE loss + seed (row f-3) ------------------------------------------------------------
+template <typename T>
+static int mse_seed(const T *states, const T *observed, const double *weights_host, T *grad_states, double *loss_out,
+                    size_t n, int steps, void *workspace, size_t ws_bytes, void *stream) {
+  if (!states || !observed || !grad_states || !loss_out || !workspace || n == 0 || steps <= 0)
+    return PDENET_E_BADARG;
+  if (steps > 64) return PDENET_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)kMseBlocks) blocks = kMseBlocks;
+  if (ws_bytes < (size_t)steps * blocks * sizeof(double)) return PDENET_E_WORKSPACE;
+  MseWeights w;
+  for (int t = 0; t < steps; ++t) w.w[t] = weights_host ? weights_host[t] : 1.0;
+  ProfScope ps(4, st);
+  mse_seed_kernel<T><<<dim3((unsigned)blocks, (unsigned)steps), 256, 0, st>>>(states, observed, grad_states,
+                                                                              (double *)workspace, n, w);
+  mse_finish_kernel<<<1, 32, 0, st>>>((const double *)workspace, (int)(steps * blocks), loss_out);
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
 // ---- FMA peak microbenchmark -----------------------------------------------------------------
 template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b) {
   T x[16];
@@ -1170,6 +1190,19 @@ int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *gra
 int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet, int B,
                             int C, int Hs, int W, int k, int N, int L, void *st) {
   return slab_bwd_end<float>(workspace, workspace_bytes, grad_kernels, grad_symnet, B, C, Hs, W, k, N, L, st);
+}
+
+int pdenet_mse_seed_f64(const double *states, const double *observed, const double *weights_host,
+                        double *grad_states, double *loss_out, size_t n_per_step, int steps, void *workspace,
+                        size_t workspace_bytes, void *st) {
+  return mse_seed<double>(states, observed, weights_host, grad_states, loss_out, n_per_step, steps, workspace,
+                          workspace_bytes, st);
+}
+int pdenet_mse_seed_f32(const float *states, const float *observed, const double *weights_host, float *grad_states,
+                        double *loss_out, size_t n_per_step, int steps, void *workspace, size_t workspace_bytes,
+                        void *st) {
+  return mse_seed<float>(states, observed, weights_host, grad_states, loss_out, n_per_step, steps, workspace,
+                         workspace_bytes, st);
 }
 
 int pdenet_profile_enable(int on) {

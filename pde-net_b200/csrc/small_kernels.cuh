@@ -34,6 +34,42 @@ template <typename T> __global__ void reduce_flat_kernel(const double *partial, 
   s = warp_sum_fixed(s);
   if (lane == 0) out[i] = (T)s;
 }
+// ---- fused MSE loss + gradient seed (row f-3) ----------------------------------------------------
+constexpr int kMseBlocks = 512; // partial sums per launch (fixed => reproducible)
+struct MseWeights {
+  double w[64];
+};
+// grid (kMseBlocks, steps): block (bx, t) strides over step t; partial[t*kMseBlocks + bx] = its sum
+template <typename T>
+__global__ void __launch_bounds__(256) mse_seed_kernel(const T *states, const T *observed, T *grad, double *partial,
+                                                       size_t n, MseWeights wts) {
+  const int t = blockIdx.y;
+  const T *s = states + (size_t)t * n, *o = observed + (size_t)t * n;
+  T *g = grad + (size_t)t * n;
+  const double scale = 2.0 * wts.w[t] / (double)n;
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double d = (double)s[i] - (double)o[i];
+    acc += d * d;
+    g[i] = (T)(scale * d);
+  }
+  __shared__ double red[8];
+  acc = warp_sum_fixed(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    partial[(size_t)t * gridDim.x + blockIdx.x] = tot * wts.w[t] / (double)n;
+  }
+}
+__global__ void mse_finish_kernel(const double *partial, int count, double *loss_out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += 32) acc += partial[i];
+  acc = warp_sum_fixed(acc);
+  if (threadIdx.x == 0) *loss_out = acc;
+}
+
 // launch geometry for the two kernels above: 4 outputs (warps) per 128-thread block
 inline unsigned reduce_blocks(int n_out) { return (unsigned)((n_out + 3) / 4); }
 

@@ -284,6 +284,38 @@ def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, 
     return out
 
 
+class _MseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, states, observed, weights):
+        states = _req(states, "states")
+        observed = _req(observed.detach(), "observed", states.dtype)
+        if states.shape != observed.shape:
+            raise ValueError("states and observed must have the same shape [steps, ...]")
+        steps = states.shape[0]
+        n = states[0].numel()
+        grad = torch.empty_like(states)
+        loss = torch.empty((), dtype=torch.float64, device=states.device)
+        ws = torch.empty(64 * 512, dtype=torch.float64, device=states.device)
+        wh = None if weights is None else (C.c_double * steps)(*[float(w) for w in weights])
+        _lib.check(_lib.fn("pdenet_mse_seed", states.dtype)(_ptr(states), _ptr(observed), wh, _ptr(grad), _ptr(loss), n,
+                                                            steps, _ptr(ws), ws.numel() * 8, _stream()),
+                   "pdenet_mse_seed")
+        ctx.save_for_backward(grad)
+        return loss.to(states.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None
+
+
+def mse_loss(states: torch.Tensor, observed: torch.Tensor, weights: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """Data term of the training loss, ``sum_t w_t * mean((states[t]-observed[t])**2)``, and its
+    gradient seed in ONE pass over the states: the returned scalar back-propagates
+    the precomputed seed into :func:`rollout`'s reverse pass."""
+    return _MseLoss.apply(states, observed, weights)
+
+
 class SlabBackward:
     """Reverse pass of a slab-decomposed rollout on one rank (C-ABI pdenet_slab_*bwd*).
 

@@ -477,6 +477,33 @@ def test_cuda_graph_capture_small_config(P, cuda_device):
     assert torch.equal(out, ref_out) and torch.equal(gm, ref_gm) and torch.equal(gs, ref_gs)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_mse_loss_seed(P, cuda_device, dtype):
+    """Fused data-term loss + seed (8f-3) == torch's mse on the oracle side, and it drives the
+    reverse rollout to the same parameter gradients."""
+    case = (5, 2, 2, 2, 3, 21, 26, 3, 0.2, 1e-2)
+    k, max_order, C, L, B, H, W, steps, dx, dt = case
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 91)
+    Ks = O.scaled_kernels(M, scales)
+    u0 = smooth_field(B, C, H, W, 92)
+    obs = torch.randn(steps, B, C, H, W, generator=torch.Generator().manual_seed(93), dtype=torch.float64)
+    wts = [1.0, 0.5, 2.0]
+    Kc, sc = Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    st = torch.stack(O.rollout(u0, Kc, sc, L, dt, steps))
+    ref = sum(w * (st[t] - obs[t]).square().mean() for t, w in enumerate(wts))
+    ref.backward()
+    Kd, sd = Ks.to(cuda_device, dtype).requires_grad_(True), sym.to(cuda_device, dtype).requires_grad_(True)
+    std = P.rollout(u0.to(cuda_device, dtype), Kd, sd, L, dt, steps)
+    loss = P.mse_loss(std, obs.to(cuda_device, dtype), wts)
+    loss.backward()
+    tol = 1e-10 * steps if dtype == torch.float64 else 2e-4
+    assert abs(loss.item() - ref.item()) < tol * abs(ref.item())
+    assert rel(Kd.grad, Kc.grad) < tol
+    assert rel(sd.grad, sc.grad) < tol
+    loss2 = P.mse_loss(std.detach(), obs.to(cuda_device, dtype), wts)
+    assert loss2.item() == loss.item()  # deterministic
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib
