@@ -83,3 +83,29 @@ def test_module_layout_and_masks(built):
     fd.grad_proj()
     assert (fd.moment.grad[fd._pinned] == 0).all() and (fd.moment.grad[~fd._pinned] == 1).all()
     assert len(list(m.diff_params())) == 6 and len(list(m.expr_params())) == 12
+
+
+def test_flat_params_view(built):
+    """FlatParams (8f-4): flat get/set round trip, x_proj after a write, grad_proj before a read."""
+    m = built.POLYPDE2D(1e-2, 0.1, 5, 2, "moment", "u,v", hidden_layers=2)
+    fp = built.FlatParams(m)
+    assert fp.numel == sum(p.numel() for p in m.parameters())
+    x = torch.arange(fp.numel, dtype=torch.float64) * 1e-3 + 5.0
+    fp.set_flat(x.numpy())
+    got = fp.get_flat()
+    # pinned moment entries were re-imposed (one-hot / zero), everything else took the new value
+    o = 0
+    for fd in m.fds:
+        blk = got[o:o + 25].reshape(5, 5)
+        assert torch.equal(blk[fd._pinned], fd._init[fd._pinned])
+        assert torch.equal(blk[~fd._pinned], x[o:o + 25].reshape(5, 5)[~fd._pinned])
+        o += 25
+    assert torch.equal(got[o:], x[o:])
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    g = fp.grad_flat()
+    o = 0
+    for fd in m.fds:
+        assert (g[o:o + 25].reshape(5, 5)[fd._pinned] == 0).all()
+        o += 25
+    assert (g[o:] == 1).all()
