@@ -218,11 +218,61 @@ class POLYPDE2D(nn.Module):
         return self.multistep(init, T)
 
 
+class LagrangeInterpFixInputs2d(nn.Module):
+    """Coefficient fields on the solver grid as piecewise tensor-product Lagrange polynomials of a
+    coarse mesh (upstream ``aTEAM.nn.modules.Interpolation.LagrangeInterpFixInputs``, SURVEY 8f-2;
+    restated from its description: the upstream source is not in the mount).
+
+    The domain ``mesh_bound = ((y0, x0), (y1, x1))`` is cut into ``mesh_size = (m0, m1)`` cells; each
+    cell carries a degree-``degree`` Lagrange basis on equispaced nodes, so the trainable table
+    ``interp_coe`` is ``[channels, m0*degree+1, m1*degree+1]``.  Because the evaluation points are
+    the fixed grid nodes, the map table -> field is two small dense matrices (built once):
+    ``field[c] = By @ interp_coe[c] @ Bx^T``.  It runs once per rollout, outside the step loop, as
+    plain tensor ops (autograd carries ``grad_coe`` from the fused reverse rollout back to the
+    table)."""
+
+    def __init__(self, channels, grid, mesh_size=(5, 5), degree=2, mesh_bound=((0.0, 0.0), (2 * math.pi, 2 * math.pi)),
+                 dtype=torch.float64):
+        super().__init__()
+        self.channels, self.grid = channels, _pair(grid)
+        self.mesh_size, self.degree, self.mesh_bound = _pair(mesh_size), int(degree), mesh_bound
+        H, W = self.grid
+        (y0, x0), (y1, x1) = mesh_bound
+        ys = y0 + (y1 - y0) * torch.arange(H, dtype=torch.float64) / H     # periodic grid: no end point
+        xs = x0 + (x1 - x0) * torch.arange(W, dtype=torch.float64) / W
+        self.register_buffer("By", self._basis(ys, y0, y1, self.mesh_size[0]).to(dtype), persistent=False)
+        self.register_buffer("Bx", self._basis(xs, x0, x1, self.mesh_size[1]).to(dtype), persistent=False)
+        self.interp_coe = nn.Parameter(torch.zeros(channels, self.mesh_size[0] * degree + 1,
+                                                   self.mesh_size[1] * degree + 1, dtype=dtype))
+
+    def _basis(self, pts: torch.Tensor, lo: float, hi: float, cells: int) -> torch.Tensor:
+        d = self.degree
+        n = cells * d + 1
+        B = torch.zeros(pts.numel(), n, dtype=torch.float64)
+        h = (hi - lo) / cells
+        for r, p in enumerate(pts.tolist()):
+            c = min(int((p - lo) / h), cells - 1)
+            t = (p - lo) / h - c                      # local coordinate in [0, 1]
+            nodes = [j / d for j in range(d + 1)]
+            for j in range(d + 1):
+                w = 1.0
+                for q in range(d + 1):
+                    if q != j:
+                        w *= (t - nodes[q]) / (nodes[j] - nodes[q])
+                B[r, c * d + j] = w
+        return B
+
+    def forward(self) -> torch.Tensor:
+        """-> coefficient fields ``[channels, H, W]`` on the solver grid."""
+        return self.By @ self.interp_coe @ self.Bx.t()
+
+
 class VariantCoeLinear2d(nn.Module):
     """PDE-Net 1 linear variable-coefficient model (row a12):
     ``u+ = D0*u + dt * sum_n c_n(x,y) (D_n*u)`` with learnable D0 and coefficient fields c_n."""
 
-    def __init__(self, kernel_size, max_order, dx, dt, mesh_size, constraint="moment", dtype=torch.float64):
+    def __init__(self, kernel_size, max_order, dx, dt, mesh_size, constraint="moment", dtype=torch.float64,
+                 interp_degree=None, interp_mesh_size=(5, 5), mesh_bound=((0.0, 0.0), (2 * math.pi, 2 * math.pi))):
         super().__init__()
         self.dt, self.dx = float(dt), _pair(dx)
         self.kernel_size, self.max_order = kernel_size, max_order
@@ -234,9 +284,14 @@ class VariantCoeLinear2d(nn.Module):
             name = "fd%d%d" % (o0, o1)
             self.add_module(name, FD2d(kernel_size, (o0, o1), dx=dx, constraint=constraint))
             self._fd_names.append(name)
-        # coefficient fields on the grid (upstream interpolates them from a coarse mesh once per
-        # call -- SURVEY "next" row f-2; here they are direct parameters)
-        self.coe = nn.Parameter(torch.zeros(len(self.orders), *self.mesh_size, dtype=torch.float64))
+        # coefficient fields on the grid: direct parameters, or (interp_degree given, as upstream)
+        # piecewise Lagrange polynomials of a coarse table evaluated once per call
+        if interp_degree is None:
+            self.interp = None
+            self.coe = nn.Parameter(torch.zeros(len(self.orders), *self.mesh_size, dtype=torch.float64))
+        else:
+            self.interp = LagrangeInterpFixInputs2d(len(self.orders), self.mesh_size, interp_mesh_size,
+                                                    interp_degree, mesh_bound)
         self.to(dtype)
 
     @property
@@ -247,7 +302,10 @@ class VariantCoeLinear2d(nn.Module):
         return (fd.moment for fd in [self.id] + self.fds)
 
     def coe_params(self):
-        return iter([self.coe])
+        return iter([self.coe] if self.interp is None else [self.interp.interp_coe])
+
+    def coefficient_fields(self) -> torch.Tensor:
+        return self.coe if self.interp is None else self.interp()
 
     def diff_x_proj(self, *a, **kw):
         for fd in [self.id] + self.fds:
@@ -265,4 +323,5 @@ class VariantCoeLinear2d(nn.Module):
 
     def forward(self, init: torch.Tensor, stepnum: int, all_states: bool = False) -> torch.Tensor:
         ks = self.scaled_kernels()
-        return ops.linear_rollout(init, ks[0], ks[1:], self.coe, self.dt, int(stepnum), last_only=not all_states)
+        return ops.linear_rollout(init, ks[0], ks[1:], self.coefficient_fields(), self.dt, int(stepnum),
+                                  last_only=not all_states)

@@ -109,3 +109,29 @@ def test_flat_params_view(built):
         assert (g[o:o + 25].reshape(5, 5)[fd._pinned] == 0).all()
         o += 25
     assert (g[o:] == 1).all()
+
+
+def test_lagrange_interp_fields(built):
+    """LagrangeInterpFixInputs2d (8f-2): partition of unity, exact reproduction of a polynomial
+    of the basis degree, continuity across cells, gradient reaches the table."""
+    import math
+    H, W, deg, mesh = 20, 24, 2, (4, 3)
+    li = built.LagrangeInterpFixInputs2d(2, (H, W), mesh, deg, ((0.0, 0.0), (2.0, 3.0)))
+    assert torch.allclose(li.By.sum(1), torch.ones(H, dtype=torch.float64), atol=1e-13)
+    assert torch.allclose(li.Bx.sum(1), torch.ones(W, dtype=torch.float64), atol=1e-13)
+    ny, nx = mesh[0] * deg + 1, mesh[1] * deg + 1
+    yn = torch.linspace(0, 2, ny, dtype=torch.float64)
+    xn = torch.linspace(0, 3, nx, dtype=torch.float64)
+    poly = lambda y, x: 1 + 2 * y - x + 0.5 * y * y + y * x - 0.25 * x * x * y * y   # degree 2 per variable
+    with torch.no_grad():
+        li.interp_coe[0] = poly(yn[:, None], xn[None, :])
+        li.interp_coe[1] = torch.sin(yn)[:, None] * torch.cos(xn)[None, :]
+    out = li()
+    yg = 2.0 * torch.arange(H, dtype=torch.float64) / H
+    xg = 3.0 * torch.arange(W, dtype=torch.float64) / W
+    assert torch.allclose(out[0], poly(yg[:, None], xg[None, :]), atol=1e-12)
+    assert (out[1] - torch.sin(yg)[:, None] * torch.cos(xg)[None, :]).abs().max() < 2e-2  # smooth field, O(h^3) with h = 1/2 .. 1
+    out.sum().backward()
+    assert li.interp_coe.grad is not None and li.interp_coe.grad.abs().sum() > 0
+    m = built.VariantCoeLinear2d(5, 2, 0.1, 1e-3, (H, W), interp_degree=2, interp_mesh_size=mesh)
+    assert m.coefficient_fields().shape == (5, H, W) and len(list(m.coe_params())) == 1

@@ -309,6 +309,37 @@ def test_linear_rollout(P, cuda_device, k, max_order, B, H, W, steps, grad_all):
         assert rel(a.grad, b.grad) < 1e-10 * steps, name
 
 
+def test_variantcoe_module_with_interpolated_fields(P, cuda_device):
+    """PDE-Net 1 model API: Lagrange-interpolated coefficient table -> fields -> fused linear
+    rollout; gradients reach the table and the moments, and match the oracle."""
+    k, max_order, H, W, steps = 5, 2, 20, 24, 3
+    dx, dt = 2 * math.pi / W, 1e-3
+    m = P.VariantCoeLinear2d(k, max_order, dx, dt, (H, W), interp_degree=2, interp_mesh_size=(4, 3)).to(cuda_device)
+    g = torch.Generator().manual_seed(33)
+    with torch.no_grad():
+        m.interp.interp_coe.copy_(torch.randn(m.interp.interp_coe.shape, generator=g, dtype=torch.float64).to(cuda_device))
+        for fd in [m.id] + m.fds:
+            fd.moment.add_((1e-3 * torch.randn(k, k, generator=g, dtype=torch.float64)).to(cuda_device))
+        m.diff_x_proj()
+    u0 = smooth_field(3, 1, H, W, 34)[:, 0].contiguous()
+    out = m(u0.to(cuda_device), steps)
+    out.square().mean().backward()
+    m.diff_grad_proj()
+    # oracle with the same numbers
+    orders = [(0, 0)] + m.orders
+    Mo = torch.stack([fd.moment.detach().cpu() for fd in [m.id] + m.fds]).requires_grad_(True)
+    table = m.interp.interp_coe.detach().cpu().requires_grad_(True)
+    Ks = O.scaled_kernels(Mo, O.filter_scales(orders, dx))
+    coe = m.interp.By.cpu() @ table @ m.interp.Bx.cpu().t()
+    ref = O.linear_rollout(u0, Ks[0], Ks[1:], coe, dt, steps)[-1]
+    ref.square().mean().backward()
+    assert rel(out, ref) < 3e-10
+    assert rel(m.interp.interp_coe.grad, table.grad) < 3e-10
+    mask = torch.stack([O.pinned_mask(k, o, "moment") for o in orders])
+    gm = torch.stack([fd.moment.grad.cpu() for fd in [m.id] + m.fds])
+    assert rel(gm, Mo.grad.masked_fill(mask, 0)) < 3e-10
+
+
 # ------------------------------------------------------------------ slab step (8e, DIST-1 on one GPU)
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_slab_step_equals_periodic_step(P, cuda_device, dtype):
