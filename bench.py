@@ -258,7 +258,8 @@ def run_ours(args):
         # one flat all-reduce of every gradient + the loss (no-op at world == 1)
         return parallel.allreduce_gradients(params, loss=loss.detach())
 
-    e2e_chunk = min(Bl, args.e2e_chunk)
+    # chunks of the streamed e2e pass: at least four per shard so the H2D copy overlaps compute
+    e2e_chunk = min(Bl, args.e2e_chunk if args.e2e_chunk > 0 else max(8, min(32, Bl // 4)))
     e2e_bufs = [stage[:e2e_chunk], torch.empty_like(stage[:e2e_chunk])]
     copy_stream = torch.cuda.Stream(dev)
 
@@ -400,7 +401,8 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override the grid side (debug only)")
     ap.add_argument("--blocks", type=int, default=0, help="override the number of dt-blocks (debug only)")
     ap.add_argument("--chunk", type=int, default=16, help="trajectories per reverse-kernel launch")
-    ap.add_argument("--e2e-chunk", type=int, default=32, help="trajectories per streamed chunk of the e2e pass")
+    ap.add_argument("--e2e-chunk", type=int, default=0,
+                    help="trajectories per streamed chunk of the e2e pass (0 = shard/4, clamped to [8, 32])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f64 = the reference's precision (default)")
     args = ap.parse_args()

@@ -137,6 +137,43 @@ CASES = [
 ]
 
 
+EDGE_CASES = [
+    # k, max_order, C, L, B, H, W, steps, dx, dt   -- degenerate / extreme shapes
+    (7, 2, 2, 2, 1, 1, 1, 2, 0.5, 1e-2),       # a single grid point: every tap wraps onto it
+    (7, 2, 2, 2, 2, 2, 3, 2, 0.5, 1e-2),       # grid smaller than the stencil
+    (5, 1, 1, 0, 1, 1, 70, 2, 0.5, 1e-2),      # one row
+    (3, 2, 3, 2, 1, 130, 1, 2, 0.5, 1e-2),     # one column, spans several tiles
+    (7, 2, 3, 2, 1, 17, 19, 2, 0.5, 1e-2),     # C*N = 18 features (32-long gradient vectors)
+    (5, 4, 1, 2, 2, 12, 66, 2, 0.7, 1e-3),     # 15 filters through the SymNet path
+    (3, 2, 1, 8, 1, 10, 11, 1, 0.5, 1e-2),     # deepest supported SymNet
+    (5, 2, 2, 2, 1, 200, 257, 1, 0.3, 1e-2),   # odd width: scalar staging path of the reverse kernels
+]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_rollout_parity_edge_shapes(P, cuda_device, case):
+    got, ref = run_both(P, cuda_device, case, torch.float64, True)
+    steps = case[7]
+    for n, a, b in zip(["states", "grad_u0", "grad_kernels", "grad_symnet"], got, ref):
+        assert rel(a, b) < TOL[torch.float64] * max(1, steps), (n, rel(a, b))
+
+
+def test_unsupported_combinations_are_refused(P, cuda_device):
+    from pdenet_b200 import _lib
+    dev = cuda_device
+    u = torch.zeros(1, 2, 8, 8, dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.PdenetError) as e:   # (N, C) = (10, 2) is not compiled
+        P.rollout(u, torch.zeros(10, 5, 5, dtype=torch.float64, device=dev),
+                  torch.zeros(2, P.symnet_param_count(20, 1), dtype=torch.float64, device=dev), 1, 1e-2, 1)
+    assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(ValueError):               # wrong SymNet length
+        P.rollout(u, torch.zeros(6, 5, 5, dtype=torch.float64, device=dev),
+                  torch.zeros(2, 10, dtype=torch.float64, device=dev), 2, 1e-2, 1)
+    with pytest.raises(TypeError):                # dtype mismatch
+        P.rollout(u, torch.zeros(6, 5, 5, dtype=torch.float32, device=dev),
+                  torch.zeros(2, 69, dtype=torch.float64, device=dev), 2, 1e-2, 1)
+
+
 def run_both(P, dev, case, dtype, grad_all, batch_chunk=0):
     k, max_order, C, L, B, H, W, steps, dx, dt = case
     orders, M, scales, sym = make_model(k, max_order, C, L, dx, 7)
