@@ -62,12 +62,44 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
   };
   const int xs = p.vec_ok ? Cfg::XS : 0; // periodic in x: a shifted tiling covers the same points
   const size_t plane = (size_t)p.g_rows * W;
-  // stage filter n of the item whose first g plane is `img0` and whose tile is (ty, tx)
+  // Staging plan (16-byte path): the global offsets of this thread's units of the tile are
+  // computed once per item (periodic wrap, clamping) and reused for all N filters of the item --
+  // per stage only an add and a cp.async per unit remain.  Unit q = tid + k*NT -> row q / UNITS.
+  constexpr int UNITS = (SC + VEC - 1) / VEC, NQ = SR * UNITS, NU = (NQ + NT - 1) / NT;
+  int goff[NU];
+  auto wrap_near = [](int v, int n) {
+    if (v < 0)
+      v += n;
+    else if (v >= n)
+      v -= n;
+    return ((unsigned)v < (unsigned)n) ? v : wrap_index(v, n);
+  };
+  auto make_plan = [&](int ty_, int tx_) {
+    const int ybase = ty_ * TH - R, xbase = tx_ * TW - xs - R;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int q = tid + k * NT, row = q / UNITS, unit = q - row * UNITS;
+      int gy = ybase + row;
+      if (p.wrap_y) gy = wrap_near(gy, H);
+      gy += p.g_off;
+      gy = gy < 0 ? 0 : (gy >= p.g_rows ? p.g_rows - 1 : gy);
+      goff[k] = gy * W + wrap_near(xbase + unit * VEC, W);
+    }
+  };
+  auto stage_plan = [&](const T *img, int gb) {
+    T *dst = gbuf + gb * TILE;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int q = tid + k * NT, row = q / UNITS, unit = q - row * UNITS;
+      if (q < NQ) cp_async_16_zfill(dst + row * PITCH + unit * VEC, img + goff[k], true);
+    }
+  };
+  // stage filter n of the item whose first g plane is `img0` and whose tile is (ty, tx); on the
+  // 16-byte path the plan must describe that tile
   auto stage_g = [&](const T *img0, int ty, int tx, int n, int gb) {
     const T *img = img0 + (size_t)n * plane;
     if (p.vec_ok)
-      stage_tile_async_vec<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
-                                                 tx * TW - xs - R, H, W);
+      stage_plan(img, gb);
     else
       stage_tile_async<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
                                              tx * TW - R, H, W);
@@ -78,6 +110,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
   int nb_ = 0, nc_ = 0, nty = 0, ntx = 0; // next item (decoded once, when its first tile is prefetched)
   if (item < p.n_items) {
     decode(item, b, c, ty, tx);
+    if (p.vec_ok) make_plan(ty, tx);
     stage_g(p.g + (size_t)(b * C + c) * N * plane, ty, tx, 0, 0);
   }
   cp_async_commit();
@@ -105,6 +138,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
         stage_g(img0, ty, tx, n + 1, gb ^ 1);
       } else if (item + (int)gridDim.x < p.n_items) {
         decode(item + gridDim.x, nb_, nc_, nty, ntx);
+        if (p.vec_ok) make_plan(nty, ntx); // every tile of the current item has been issued
         stage_g(p.g + (size_t)(nb_ * C + nc_) * N * plane, nty, ntx, 0, gb ^ 1);
       }
       cp_async_commit();
