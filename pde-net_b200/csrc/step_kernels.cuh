@@ -3,10 +3,11 @@
 // adjoints g and reduce the SymNet parameter gradients).
 //
 // Restates SURVEY.md section 8(a) rows a5-a9 (forward) and the SymNet half of a11 (reverse).
-// Thread mapping: one warp = 32 consecutive x; a thread owns a vertical strip of P=4 points and
-// keeps all N derivative accumulators of that strip in registers, so one staged u value feeds
-// N*min(P,K) FMAs and one broadcast weight feeds P FMAs (shared-memory wavefronts ~0.5/cycle/SM at
-// fp64 DFMA peak).
+// Thread mapping: one warp = 32 consecutive x; a thread owns a vertical strip of P points (4 in
+// fp64, 8 in fp32) and keeps all N derivative accumulators of that strip in registers, so one
+// staged u value feeds N*min(P,K) FMAs; the filter taps come from constant memory through uniform
+// registers (`DFMA R, R, UR, R`: two vector-register operands per FMA, the only way to the full
+// FP64 rate on B200 -- DESIGN.md section 3) and each feeds P FMAs.
 #pragma once
 #include "common.cuh"
 #include "params.cuh"
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, L = p.L, Psym = p.Psym;
 
-  // ---- one-time setup: weights (tap-major, filters innermost) and SymNet parameters
+  // ---- one-time setup: SymNet parameters to shared memory, zeroed gradient accumulators
   if (!LINEAR)
     for (int idx = tid; idx < Cfg::sym_elems(Psym); idx += NT) syms[idx] = idx < C * Psym ? p.symnet[idx] : T(0);
   if (WITH_GRAD)
