@@ -585,6 +585,27 @@ def test_lbfgs_training_loop_reduces_loss(P, cuda_device):
     assert fmin < 5e-2 * f0, (f0, fmin)  # measured: 2.6e-3 -> 1.7e-5 after 120 iterations
 
 
+def test_concurrent_streams_use_separate_constant_slots(P, cuda_device):
+    """Two rollouts with DIFFERENT filter banks issued back to back on two streams must not see
+    each other's taps (the taps live in a ring of constant-memory slots guarded by events)."""
+    k, max_order, C, L, dx, dt, steps = 7, 2, 2, 2, 0.1, 1e-3, 2
+    models = [make_model(k, max_order, C, L, dx, seed) for seed in (101, 202, 303)]
+    u = smooth_field(4, C, 96, 128, 104).to(cuda_device)
+    Ks = [O.scaled_kernels(M, sc).to(cuda_device) for (_, M, sc, _) in models]
+    syms = [sym.to(cuda_device) for (_, _, _, sym) in models]
+    ref = [P.rollout(u, Ks[i], syms[i], L, dt, steps, last_only=True).clone() for i in range(3)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(5):
+        outs = [None] * 3
+        for i, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                outs[i] = P.rollout(u, Ks[i], syms[i], L, dt, steps, last_only=True)
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert torch.equal(outs[i], ref[i]), (rep, i)
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib
