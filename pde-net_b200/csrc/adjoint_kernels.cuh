@@ -259,11 +259,7 @@ template <typename T, int K> struct FGradCfg {
   static constexpr int NT = 192; // 6 warps, 2 CTAs per SM
   static constexpr int GST_ELEMS = RW * 32 * VEC; // per-warp g micro-tile staging (single buffer: it is
                                                   // drained into registers before the next copy is issued)
-  // With 16-byte staging the tile is shifted left by XS columns (see AdjCfg).
-  static constexpr int XS = (VEC - R % VEC) % VEC;
-  static __host__ size_t smem_bytes() {
-    return (size_t)(2 * TILE_ELEMS + (NT / 32) * GST_ELEMS) * sizeof(T) + 2 * sizeof(unsigned long long) + 2 * sizeof(int);
-  }
+  static __host__ size_t smem_bytes() { return (size_t)(2 * TILE_ELEMS + (NT / 32) * GST_ELEMS) * sizeof(T); }
 };
 
 template <typename T, int K>
@@ -278,28 +274,10 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
   T *ubuf = reinterpret_cast<T *>(smem_raw); // [2][SR][PITCH]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = NTHREADS / 32;
   T *gst = ubuf + 2 * TILE + warp * Cfg::GST_ELEMS + lane * VEC; // [RW][32 lanes][VEC], this lane's slots
-  // synchronisation state after the tiles and the g staging slots: two "tile landed" mbarriers and
-  // two "warps finished with this buffer" counters -- there is NO block barrier in the item loop
-  unsigned long long *ready = reinterpret_cast<unsigned long long *>(ubuf + 2 * TILE + NW * Cfg::GST_ELEMS);
-  int *done = reinterpret_cast<int *>(ready + 2);
   const int H = p.H, W = p.W, N = p.N, C = p.C;
-  const int parts = NW / p.nw, part = warp / p.nw;
+  const int parts = (NTHREADS / 32) / p.nw, part = warp / p.nw;
   const int n = p.n0 + warp % p.nw;
-  const bool bulk = p.vec_ok != 0;
-  // 16-byte path: tiling shifted left by XS so that the u window start is 16-byte aligned
-  const int xs = bulk ? Cfg::XS : 0;
-  constexpr int UNITS = (SC + VEC - 1) / VEC, ROW_ELEMS = UNITS * VEC;
-  static_assert(ROW_ELEMS <= PITCH && (PITCH * sizeof(T)) % 16 == 0, "bulk rows need a 16-byte pitch");
-
-  if (tid == 0) {
-    mbar_init(ready, bulk ? 1 : 32);
-    mbar_init(ready + 1, bulk ? 1 : 32);
-    done[0] = done[1] = 0;
-    mbar_fence_init();
-  }
-  __syncthreads();
 
   auto decode = [&](int item, int &b, int &c, int &ty, int &tx) {
     tx = item % p.tiles_x;
@@ -309,112 +287,71 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
     c = t % C;
     b = t / C;
   };
-  auto wrap_near = [](int v, int nn) {
-    if (v < 0)
-      v += nn;
-    else if (v >= nn)
-      v -= nn;
-    return ((unsigned)v < (unsigned)nn) ? v : wrap_index(v, nn);
-  };
-  // Stage the u tile (+halo) of `item` into buffer ub.  Executed by ONE warp (all 32 lanes).
   auto stage_u = [&](int item, int ub) {
     int b, c, ty, tx;
     decode(item, b, c, ty, tx);
-    const T *img = p.u + (size_t)(b * C + c) * p.u_rows * W;
-    T *dst = ubuf + ub * TILE;
-    if (bulk) {
-      // one bulk copy per tile row (two where the row crosses the periodic seam), TMA engine
-      fence_proxy_async();
-      if (lane == 0) mbar_expect_tx(ready + ub, (unsigned)(SR * ROW_ELEMS * sizeof(T)));
-      __syncwarp();
-      for (int row = lane; row < SR; row += 32) {
-        int gy = ty * TH - R + row;
-        if (p.wrap_y) gy = wrap_near(gy, H);
-        gy += p.u_off;
-        gy = gy < 0 ? 0 : (gy >= p.u_rows ? p.u_rows - 1 : gy);
-        const T *srow = img + (size_t)gy * W;
-        int gx = wrap_near(tx * TW - xs - R, W), filled = 0;
-        while (filled < ROW_ELEMS) {
-          int len = W - gx;
-          if (len > ROW_ELEMS - filled) len = ROW_ELEMS - filled;
-          bulk_copy_g2s(dst + row * PITCH + filled, srow + gx, (unsigned)(len * sizeof(T)), ready + ub);
-          filled += len;
-          gx = 0;
-        }
-      }
-    } else {
-      // generic path: element copies by this warp, arrival when each lane's copies have landed
-      constexpr int NCB = (SC + 31) / 32;
-      int gx[NCB];
-#pragma unroll
-      for (int j = 0; j < NCB; ++j) gx[j] = wrap_index(tx * TW - R + lane + 32 * j, W);
-      for (int row = 0; row < SR; ++row) {
-        int gy = ty * TH - R + row;
-        if (p.wrap_y) gy = wrap_near(gy, H);
-        gy += p.u_off;
-        gy = gy < 0 ? 0 : (gy >= p.u_rows ? p.u_rows - 1 : gy);
-        const T *srow = img + (size_t)gy * W;
-#pragma unroll
-        for (int j = 0; j < NCB; ++j) {
-          const int lx = lane + 32 * j;
-          if (lx < SC) cp_async_elem(dst + row * PITCH + lx, srow + gx[j]);
-        }
-      }
-      cp_async_mbar_arrive(ready + ub);
-    }
+    stage_tile_async<T, SR, SC, PITCH, NTHREADS>(ubuf + ub * TILE, p.u + (size_t)(b * C + c) * p.u_rows * W,
+                                                 p.u_rows, p.u_off, p.wrap_y, ty * TH - R, tx * TW - R, H, W);
   };
 
   T kacc[VLB];
 #pragma unroll
   for (int e = 0; e < VLB; ++e) kacc[e] = T(0);
 
-  // prologue: the first two items' tiles (both buffers are free)
-  if (warp == 0) {
-    if ((int)blockIdx.x < p.n_items) stage_u(blockIdx.x, 0);
-    if ((int)(blockIdx.x + gridDim.x) < p.n_items) stage_u(blockIdx.x + gridDim.x, 1);
-  }
+  int item = blockIdx.x, ub = 0;
+  if (item < p.n_items) stage_u(item, 0);
+  cp_async_commit();
 
-  unsigned rphase[2] = {0u, 0u};
-  int ub = 0;
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    // this item's tile has landed (it was issued when the last warp finished the item two back)
-    mbar_wait(ready + ub, rphase[ub]);
-    rphase[ub] ^= 1u;
+  for (; item < p.n_items; item += gridDim.x) {
+    // One barrier per item: every cp.async group issued so far (this item's u tile, issued one item
+    // ago) has landed, and every warp has finished the previous item, so the other u buffer is
+    // free for the next prefetch.
+    cp_async_wait<0>();
+    __syncthreads();
+
     {
       int b, c, ty, tx;
       decode(item, b, c, ty, tx);
-      const int x0 = tx * TW - xs + lane * VEC; // in [-xs, W - xs) for valid columns
-      const T *gimg = p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W + (size_t)p.g_off * W;
+      const int x0 = tx * TW + lane * VEC;
+      const T *gimg = p.g + (size_t)((b * C + c) * N + n) * p.g_rows * W;
       const T *us = ubuf + ub * TILE + lane * VEC;
-      int xg[VEC];
-      bool okc[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        okc[i] = (x0 + i) < W - xs;
-        xg[i] = okc[i] ? ((x0 + i) < 0 ? x0 + i + W : x0 + i) : 0;
-      }
 
-      // g micro-tile: global -> this lane's staging slots (cp.async, zero-filled outside the
-      // domain), one micro-tile ahead of the compute.  With the shifted tiling the columns are
-      // not 16-byte aligned any more: element copies.
+      // g micro-tile: global -> this warp's staging slots (cp.async, zero-filled outside the
+      // domain), one micro-tile ahead of the compute
+      const bool okx = x0 < W;
+      const T *gcol = gimg + (size_t)p.g_off * W + (okx ? x0 : 0);
       auto stage_g = [&](int mt) {
         const int ybase = ty * TH + mt * RW;
+        const T *grow = gcol + (size_t)ybase * W;
 #pragma unroll
         for (int j = 0; j < RW; ++j) {
-          const bool oky = ybase + j < H;
-          const T *grow = gimg + (size_t)(oky ? ybase + j : 0) * W;
+          const bool ok = okx && (ybase + j < H);
+          const T *src = ok ? grow + (size_t)j * W : gcol;
           T *dst = gst + j * 32 * VEC;
+          if (p.vec_ok) {
+            cp_async_16_zfill(dst, src, ok);
+          } else {
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) cp_async_elem_zfill(dst + i, grow + xg[i], oky && okc[i]);
+            for (int i = 0; i < VEC; ++i) dst[i] = (ok && x0 + i < W) ? src[i] : T(0);
+          }
         }
       };
 
+      // cp.async group order per item: G(first), U(next item), then G(mt+1) right after G(mt) has
+      // been drained into registers -- the staging slots are single-buffered and lane-private.
       stage_g(part);
       cp_async_commit();
+      if (item + (int)gridDim.x < p.n_items) stage_u(item + gridDim.x, ub ^ 1);
+      cp_async_commit();
+      bool first = true;
 #pragma unroll 1
       for (int mt = part; mt < MT; mt += parts) {
         if (ty * TH + mt * RW >= H) break; // warp-uniform: nothing left in this tile
-        cp_async_wait<0>();
+        if (first)
+          cp_async_wait<1>(); // G(first) landed; U(next) may still be in flight
+        else
+          cp_async_wait<0>();
+        first = false;
         T gc[RW][VEC];
 #pragma unroll
         for (int j = 0; j < RW; ++j) ld_vec(gst + j * 32 * VEC, &gc[j][0]);
@@ -440,22 +377,6 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
             }
         }
       }
-      cp_async_wait<0>();
-    }
-    // Done with buffer ub.  The LAST warp to get here refills it with the tile two items ahead:
-    // nobody ever waits for a slower warp, the ring of two buffers gives one item of slack.
-    __syncwarp();
-    int last = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      last = (atomicAdd(&done[ub], 1) == NW - 1);
-      if (last) done[ub] = 0;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence_block();
-      const int nxt = item + 2 * gridDim.x;
-      if (nxt < p.n_items) stage_u(nxt, ub);
     }
     ub ^= 1;
   }

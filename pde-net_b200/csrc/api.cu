@@ -319,8 +319,7 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
   p.tiles_y = (H + th - 1) / th;
   p.n_items = B * C * p.tiles_x * p.tiles_y;
   const int vec = 16 / (int)sizeof(T);
-  // 16-byte path: the u tile rows are staged with bulk copies (needs aligned rows)
-  p.vec_ok = (W % vec == 0) && (((uintptr_t)p.u) % 16 == 0) ? 1 : 0;
+  p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   const int cap = sms * kFGradCtasPerSm;

@@ -75,17 +75,6 @@ __device__ __forceinline__ void cp_async_16_zfill(void *smem, const void *gmem, 
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
 }
-// element copy, zero-filled when !valid
-__device__ __forceinline__ void cp_async_elem_zfill(double *smem, const double *gmem, bool valid) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int bytes = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
-}
-__device__ __forceinline__ void cp_async_elem_zfill(float *smem, const float *gmem, bool valid) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int bytes = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
@@ -108,11 +97,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsign
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// arrival on `bar` once every cp.async this thread has issued so far has completed
-__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
   asm volatile("{\n"
                ".reg .pred p;\n"

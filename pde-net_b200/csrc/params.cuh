@@ -70,7 +70,7 @@ template <typename T> struct FGradParams {
   double *dk_partial; // [gridDim.x * 6][N][VLB], accumulated across launches
   int n0, nw;         // this launch handles filters n0 .. n0+nw-1; warp w -> filter n0 + w % nw,
                       // row part w / nw of `parts` = NWARPS / nw (nw divides NWARPS)
-  int vec_ok;         // 1 if u rows may be staged with 16-byte bulk copies (W % VEC == 0, base aligned)
+  int vec_ok;         // 1 if g rows may be read with 16-byte loads (W % VEC == 0, base aligned)
   int B, C, N, H, W;
   int tiles_x, tiles_y, n_items;
 };
