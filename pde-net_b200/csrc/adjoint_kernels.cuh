@@ -36,7 +36,7 @@ template <typename T, int K> struct AdjCfg {
   static constexpr int KKP = round_up(KK, VEC);
   static constexpr int VLB = KK <= 16 ? 16 : (KK <= 32 ? 32 : 64);
   static constexpr int TILE_ELEMS = SR * PITCH;
-  static __host__ size_t smem_bytes(int) { return (size_t)(2 * TILE_ELEMS) * sizeof(T) + 16; } // + 2 mbarriers
+  static __host__ size_t smem_bytes(int) { return (size_t)(2 * TILE_ELEMS) * sizeof(T); }
 };
 
 template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_kernel(const AdjParams<T> p) {
@@ -62,20 +62,11 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
   };
   const int xs = p.vec_ok ? Cfg::XS : 0; // periodic in x: a shifted tiling covers the same points
   const size_t plane = (size_t)p.g_rows * W;
-  // 16-byte path: every tile row (+halo) is one or two contiguous, 16-byte-aligned segments in
-  // global memory (two when the row crosses the periodic seam), so the tile is staged with
-  // cp.async.bulk row copies issued by a handful of threads and completed on an mbarrier: no
-  // per-element LDGSTS, the LSU stays free for the window reads.
-  constexpr int UNITS = (SC + VEC - 1) / VEC, ROW_ELEMS = UNITS * VEC;
-  static_assert(ROW_ELEMS <= PITCH && (PITCH * sizeof(T)) % 16 == 0, "bulk rows need 16-byte pitch");
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbuf + 2 * TILE); // [2]
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    mbar_init(mbar + 1, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  unsigned mphase[2] = {0u, 0u};
+  // Staging plan (16-byte path): the global offsets of this thread's units of the tile are
+  // computed once per item (periodic wrap, clamping) and reused for all N filters of the item --
+  // per stage only an add and a cp.async per unit remain.  Unit q = tid + k*NT -> row q / UNITS.
+  constexpr int UNITS = (SC + VEC - 1) / VEC, NQ = SR * UNITS, NU = (NQ + NT - 1) / NT;
+  int goff[NU];
   auto wrap_near = [](int v, int n) {
     if (v < 0)
       v += n;
@@ -83,27 +74,24 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
       v -= n;
     return ((unsigned)v < (unsigned)n) ? v : wrap_index(v, n);
   };
-  auto stage_bulk = [&](const T *img, int ty_, int tx_, int gb) {
-    if (tid == 0) mbar_expect_tx(mbar + gb, (unsigned)(SR * ROW_ELEMS * sizeof(T)));
-    if (tid < SR) { // one thread per tile row
-      const int row = tid;
-      int gy = ty_ * TH - R + row;
+  auto make_plan = [&](int ty_, int tx_) {
+    const int ybase = ty_ * TH - R, xbase = tx_ * TW - xs - R;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int q = tid + k * NT, row = q / UNITS, unit = q - row * UNITS;
+      int gy = ybase + row;
       if (p.wrap_y) gy = wrap_near(gy, H);
       gy += p.g_off;
       gy = gy < 0 ? 0 : (gy >= p.g_rows ? p.g_rows - 1 : gy);
-      const int gx0 = wrap_near(tx_ * TW - xs - R, W); // multiple of VEC
-      const T *srow = img + (size_t)gy * W;
-      T *drow = gbuf + gb * TILE + row * PITCH;
-      int done = 0;
-      // split at the periodic seam(s); W % VEC == 0 keeps every piece 16-byte aligned
-      int gx = gx0;
-      while (done < ROW_ELEMS) {
-        int len = W - gx;
-        if (len > ROW_ELEMS - done) len = ROW_ELEMS - done;
-        bulk_copy_g2s(drow + done, srow + gx, (unsigned)(len * sizeof(T)), mbar + gb);
-        done += len;
-        gx = 0;
-      }
+      goff[k] = gy * W + wrap_near(xbase + unit * VEC, W);
+    }
+  };
+  auto stage_plan = [&](const T *img, int gb) {
+    T *dst = gbuf + gb * TILE;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int q = tid + k * NT, row = q / UNITS, unit = q - row * UNITS;
+      if (q < NQ) cp_async_16_zfill(dst + row * PITCH + unit * VEC, img + goff[k], true);
     }
   };
   // stage filter n of the item whose first g plane is `img0` and whose tile is (ty, tx); on the
@@ -111,7 +99,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
   auto stage_g = [&](const T *img0, int ty, int tx, int n, int gb) {
     const T *img = img0 + (size_t)n * plane;
     if (p.vec_ok)
-      stage_bulk(img, ty, tx, gb);
+      stage_plan(img, gb);
     else
       stage_tile_async<T, SR, SC, PITCH, NT>(gbuf + gb * TILE, img, p.g_rows, p.g_off, p.wrap_y, ty * TH - R,
                                              tx * TW - R, H, W);
@@ -122,6 +110,7 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
   int nb_ = 0, nc_ = 0, nty = 0, ntx = 0; // next item (decoded once, when its first tile is prefetched)
   if (item < p.n_items) {
     decode(item, b, c, ty, tx);
+    if (p.vec_ok) make_plan(ty, tx);
     stage_g(p.g + (size_t)(b * C + c) * N * plane, ty, tx, 0, 0);
   }
   cp_async_commit();
@@ -143,17 +132,13 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
       // One barrier per stage: after it, this stage's tile has landed for every thread AND every
       // warp has finished the previous stage, so the other buffer is free for the next prefetch
       // (next filter of this item, or the first filter of the next item).
-      if (p.vec_ok) {
-        mbar_wait(mbar + gb, mphase[gb]);
-        mphase[gb] ^= 1u;
-      } else {
-        cp_async_wait<0>();
-      }
+      cp_async_wait<0>();
       __syncthreads();
       if (n + 1 < N) {
         stage_g(img0, ty, tx, n + 1, gb ^ 1);
       } else if (item + (int)gridDim.x < p.n_items) {
         decode(item + gridDim.x, nb_, nc_, nty, ntx);
+        if (p.vec_ok) make_plan(nty, ntx); // every tile of the current item has been issued
         stage_g(p.g + (size_t)(nb_ * C + nc_) * N * plane, nty, ntx, 0, gb ^ 1);
       }
       cp_async_commit();

@@ -80,36 +80,6 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// ---- bulk asynchronous copy (TMA engine, UBLKCP) + mbarrier --------------------------------------
-// One instruction moves a whole 16-byte-aligned row segment global -> shared; completion is
-// signalled as transaction bytes on an mbarrier, so no per-element LDGSTS issue slots are spent.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile("{\n"
-               ".reg .pred p;\n"
-               "WAIT_%=:\n"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-               "@p bra DONE_%=;\n"
-               "bra WAIT_%=;\n"
-               "DONE_%=:\n"
-               "}\n" ::"r"(smem_u32(bar)),
-               "r"(parity)
-               : "memory");
-}
-
 // Stage a ROWS x COLS window of one image (origin (y0, x0) in logical coordinates, periodic in x,
 // periodic in y iff wrap_y) into shared memory with row pitch PITCH.  All NT threads take part;
 // lanes run along x so global reads are coalesced.
