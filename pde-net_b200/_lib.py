@@ -68,9 +68,17 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                "pdenet_b200: %s is missing -- build it with `python pde-net_b200/build.py` "
-                "(there is no CPU fallback)" % LIB_PATH)
+            # not a fallback: compile the CUDA library in place (nvcc, sm_100a) or fail loudly
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("pdenet_b200_build", os.path.join(_HERE, "build.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    "pdenet_b200: %s is missing and could not be built (%s) -- build it with "
+                    "`python pde-net_b200/build.py` (there is no CPU fallback)" % (LIB_PATH, e)) from e
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in _PROTOS.items():
             for n in ([name.format(t="f64"), name.format(t="f32")] if "{t}" in name else [name]):
