@@ -45,6 +45,14 @@ KERNEL_NAMES = {"fwd_step": "step_kernel<double,7,6,2,MODE_FWD> (fused stencils+
                 "bwd_kernel_A": "step_kernel<double,7,6,2,MODE_BWD_A> (recompute + SymNet reverse)",
                 "bwd_kernel_B1": "adjoint_kernel<double,7> (data gradient)",
                 "bwd_kernel_B2": "filter_grad_kernel<double,7> (filter gradient)"}
+# algorithmic HBM bytes per grid point of each kernel (fp64)
+KERNEL_BYTES = {"fwd_step": 32.0, "bwd_kernel_A": 128.0, "bwd_kernel_B1": 128.0, "bwd_kernel_B2": 112.0}
+# with kept features (ops.rollout keep_features): the forward step also writes the 12 feature planes,
+# kernel A reads them back instead of recomputing the stencils
+KEPT_FLOPS = {"bwd_kernel_A": 788.0}       # SymNet recompute 260 + data and parameter gradient 2*264
+KEPT_BYTES = {"fwd_step": 128.0, "bwd_kernel_A": 208.0}
+KEPT_NAMES = {"fwd_step": "step_kernel<double,7,6,2,MODE_FWD> (fused stencils+SymNet+Euler, features kept)",
+              "bwd_kernel_A": "step_kernel<double,7,6,2,MODE_BWD_A_KEPT> (SymNet reverse on kept features)"}
 BYTES_PER_POINT_STEP = 80.0  # 5*C*s
 NOMINAL_FP64_TFLOPS = 37.0
 
@@ -226,8 +234,16 @@ def run_ours(args):
     dt = 0.25 * dx * dx
     chunk = min(Bl, args.chunk)
 
+    pass_chunk = Bl if args.pass_chunk <= 0 else min(Bl, args.pass_chunk)
+    keep = args.keep == "on" and pass_chunk * blocks * C * len(P.order_list(CFG["max_order"])) * H * W \
+        * (8 if args.dtype == "f64" else 4) <= ops.FEATURE_CACHE_BYTES
+    kflops, kbytes, knames = dict(KERNEL_FLOPS), dict(KERNEL_BYTES), dict(KERNEL_NAMES)
+    if keep:
+        kflops.update(KEPT_FLOPS)
+        kbytes.update(KEPT_BYTES)
+        knames.update(KEPT_NAMES)
     model = P.POLYPDE2D(dt, dx, k, CFG["max_order"], "moment", "u,v", hidden_layers=L, batch_chunk=chunk,
-                        dtype=dtype).to(dev)
+                        dtype=dtype, keep_features=keep).to(dev)
     orders, M, scales, sym = model_params(k, CFG["max_order"], C, L, dx)
     with torch.no_grad():
         for fd, m in zip(model.fds, M):
@@ -251,12 +267,12 @@ def run_ours(args):
     def one_pass(inp):
         for p in params:
             p.grad = None
-        out = model(inp, blocks * dt)
-        loss = out.square().mean() / world
-        loss.backward()
+        # the shard goes through the rollout `pass_chunk` trajectories at a time (bounds the live
+        # states + kept features); loss = mean square of the final states over the global batch
+        loss = parallel.chunked_fwd_bwd(model, inp, blocks * dt, 1.0 / (inp[0].numel() * B), pass_chunk)
         model.diff_grad_proj()
         # one flat all-reduce of every gradient + the loss (no-op at world == 1)
-        return parallel.allreduce_gradients(params, loss=loss.detach())
+        return parallel.allreduce_gradients(params, loss=loss)
 
     # chunks of the streamed e2e pass: at least four per shard so the H2D copy overlaps compute
     e2e_chunk = min(Bl, args.e2e_chunk if args.e2e_chunk > 0 else max(8, min(32, Bl // 4)))
@@ -338,15 +354,26 @@ def run_ours(args):
     e2e = pts * args.steps / (ms_e2e * 1e-3)
     hbm_peak, hbm_src = peaks()
     # dominant kernel = the kind with the largest share of the timed region
-    top = max(KERNEL_FLOPS, key=lambda kk: kind_ms[kk])
+    top = max(kflops, key=lambda kk: kind_ms[kk])
     n_top = max(1, kind_n[top])
     ms_top = kind_ms[top] / n_top
-    pts_per_launch = (Bl * H * W) if top == "fwd_step" else (chunk * H * W)
-    achieved = KERNEL_FLOPS[top] * pts_per_launch / (ms_top * 1e-3) / 1e12
-    per_kernel = {kk: {"ms_per_launch": kind_ms[kk] / max(1, kind_n[kk]), "launches": kind_n[kk],
-                       "tflops": KERNEL_FLOPS[kk] * ((Bl if kk == "fwd_step" else chunk) * H * W)
-                       / (kind_ms[kk] / max(1, kind_n[kk]) * 1e-3) / 1e12 if kind_ms[kk] > 0 else None}
-                  for kk in KERNEL_FLOPS}
+    es = 8 if args.dtype == "f64" else 4
+
+    def launch_pts(kk):  # grid points one launch of this kernel covers
+        return (pass_chunk if kk == "fwd_step" else min(chunk, pass_chunk)) * H * W
+
+    pts_per_launch = launch_pts(top)
+    achieved = kflops[top] * pts_per_launch / (ms_top * 1e-3) / 1e12
+    per_kernel = {}
+    for kk in kflops:
+        if kind_ms[kk] <= 0:
+            continue
+        sec = kind_ms[kk] / max(1, kind_n[kk]) * 1e-3
+        per_kernel[kk] = {"ms_per_launch": sec * 1e3, "launches": kind_n[kk],
+                          "tflops": kflops[kk] * launch_pts(kk) / sec / 1e12,
+                          "frac_of_fma_peak": kflops[kk] * launch_pts(kk) / sec / fma_peak,
+                          "algorithmic_gbs": kbytes[kk] * es / 8 * launch_pts(kk) / sec / 1e9,
+                          "frac_of_hbm_peak": kbytes[kk] * es / 8 * launch_pts(kk) / sec / 1e9 / hbm_peak}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -362,6 +389,7 @@ def run_ours(args):
         "config": {"workload": CFG["workload"] if args.dtype == "f64" else CFG["workload"].replace("fp64", "fp32"),
                    "global_batch": B, "per_gpu_batch": Bl, "grid": [H, W],
                    "dt_blocks": blocks, "max_order": CFG["max_order"], "dt": dt, "batch_chunk": chunk,
+                   "pass_chunk": pass_chunk, "features": "kept in HBM for the reverse pass" if keep else "recomputed",
                    "parallelism": "dp%d (batch-sharded, one NCCL all-reduce of %d grad scalars)" % (world, nparam + 1),
                    "l2": "inputs (%.1f GB per pass) larger than L2; no flush needed" % (u0.numel() * 8 / 1e9)},
         "e2e": {"value": e2e, "unit": "grid-point-steps/s", "h2d_bytes_per_step": u0.numel() * u0.element_size(),
@@ -371,10 +399,10 @@ def run_ours(args):
         "gpu_launches": int(sum(kind_n.values())),
         "clocks": clocks,
         "roofline": {
-            "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": KERNEL_NAMES[top].replace("double", "double" if args.dtype == "f64" else "float"),
+            "bound": "fp64" if args.dtype == "f64" else "fp32", "kernel": knames[top].replace("double", "double" if args.dtype == "f64" else "float"),
             "achieved": achieved, "peak": fma_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fma_peak / 1e12),
             "peak_source": "measured this run: pdenet_fma_peak register-only DFMA loop (nominal %.0f)" % NOMINAL_FP64_TFLOPS,
-            "flops_per_launch": KERNEL_FLOPS[top] * pts_per_launch, "ms_per_launch": ms_top, "launches": n_top,
+            "flops_per_launch": kflops[top] * pts_per_launch, "ms_per_launch": ms_top, "launches": n_top,
             "traffic": traffic, "per_kernel": per_kernel, "fma_probe_tflops": fma_probe,
             "kernel_ms_share": {kk: (v / total_kernel_ms if total_kernel_ms else None) for kk, v in kind_ms.items()},
             "whole_pass": {"flop_per_point_step": F_TOTAL, "achieved_tflops": F_TOTAL * value / 1e12 / world,
@@ -401,6 +429,10 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override the grid side (debug only)")
     ap.add_argument("--blocks", type=int, default=0, help="override the number of dt-blocks (debug only)")
     ap.add_argument("--chunk", type=int, default=16, help="trajectories per reverse-kernel launch")
+    ap.add_argument("--pass-chunk", type=int, default=32,
+                    help="trajectories per forward+reverse rollout of the resident pass (0 = the whole shard)")
+    ap.add_argument("--keep", choices=["on", "off"], default="on",
+                    help="keep the derivative features of each chunk for the reverse pass (off = recompute)")
     ap.add_argument("--e2e-chunk", type=int, default=0,
                     help="trajectories per streamed chunk of the e2e pass (0 = shard/4, clamped to [8, 32])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

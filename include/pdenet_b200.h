@@ -115,6 +115,29 @@ PDENET_API int pdenet_rollout_bwd_f32(const float *u0, const float *states, cons
                            float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
                            int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
 
+/* Feature-keeping variant of the rollout (same results, bit for bit; trades HBM for FP64 work).
+ * pdenet_rollout_fwd_keep_* additionally stores the C*N derivative features of every step's
+ * INPUT state: feats[t] = FD bank applied to u_t, t = 0..steps-1, layout [steps][B][C*N][H][W]
+ * (what the reference's autograd keeps alive as conv2d outputs, polypde.py::UInputs [RECALL]).
+ * pdenet_rollout_bwd_kept_* reads them, so its first reverse kernel runs only the SymNet
+ * reverse sweep instead of recomputing the stencils.  Everything else as the plain pair above. */
+PDENET_API int pdenet_rollout_fwd_keep_f64(const double *u0, const double *kernels, const double *symnet, double *states,
+                                double *feats, int B, int C, int H, int W, int k, int N, int L, int steps, double dt,
+                                void *stream);
+PDENET_API int pdenet_rollout_fwd_keep_f32(const float *u0, const float *kernels, const float *symnet, float *states,
+                                float *feats, int B, int C, int H, int W, int k, int N, int L, int steps, double dt,
+                                void *stream);
+PDENET_API int pdenet_rollout_bwd_kept_f64(const double *u0, const double *states, const double *feats,
+                                const double *grad_states, int grad_mode, const double *kernels,
+                                const double *symnet, double *grad_u0, double *grad_kernels, double *grad_symnet,
+                                void *workspace, size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W,
+                                int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API int pdenet_rollout_bwd_kept_f32(const float *u0, const float *states, const float *feats, const float *grad_states,
+                                int grad_mode, const float *kernels, const float *symnet, float *grad_u0,
+                                float *grad_kernels, float *grad_symnet, void *workspace, size_t workspace_bytes,
+                                int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
+                                double dt, void *stream);
+
 /* ---- row a12: PDE-Net 1 linear variable-coefficient rollout (VariantCoeLinear2d.forward) ----
  * u_{t+1} = K0 (*) u_t + dt * sum_n coe[n,y,x] * (kernels[n] (*) u_t);  u: [B,H,W],
  * coe: [N,H,W], id_kernel K0: [k,k].  grad_coe is [N,H,W]. */

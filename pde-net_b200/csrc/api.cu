@@ -274,7 +274,7 @@ static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int
   p.W = W;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  ProfScope ps((mode == MODE_BWD_A || mode == MODE_LIN_BWD_A) ? 1 : 0, st);
+  ProfScope ps((mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT || mode == MODE_LIN_BWD_A) ? 1 : 0, st);
   return launch_step<T, K>(mode, N, C, VL, p, sms, st);
 }
 
@@ -340,8 +340,8 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
 
 // ---- forward rollout (rows a5-a10) -----------------------------------------------------------
 template <typename T>
-static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states, int B, int C, int H, int W, int k,
-                       int N, int L, int steps, double dt, void *stream) {
+static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states, T *feats, int B, int C, int H,
+                       int W, int k, int N, int L, int steps, double dt, void *stream) {
   if (!u0 || !kernels || !symnet || !states || bad_geom(B, C, H, W, k, N) || L < 0 || steps < 0)
     return PDENET_E_BADARG;
   if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
@@ -360,6 +360,7 @@ static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states
   for (int t = 0; t < steps; ++t) {
     p.u = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
     p.out = states + (size_t)t * stride;
+    p.feats = feats ? feats + (size_t)t * stride * N : nullptr; // features of the step's input state u_t
     int rc = 0;
     PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, H, W, (cudaStream_t)stream)));
     if (rc) return rc;
@@ -626,8 +627,8 @@ static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N,
 }
 
 template <typename T>
-static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int grad_mode, const T *kernels,
-                       const T *symnet, T *grad_u0, T *grad_kernels, T *grad_symnet, void *workspace,
+static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *grad_states, int grad_mode,
+                       const T *kernels, const T *symnet, T *grad_u0, T *grad_kernels, T *grad_symnet, void *workspace,
                        size_t ws_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
                        double dt, void *stream) {
   if (!u0 || !grad_states || !kernels || !symnet || !workspace || bad_geom(B, C, H, W, k, N) || L < 0 ||
@@ -680,8 +681,12 @@ static int rollout_bwd(const T *u0, const T *states, const T *grad_states, int g
       p.g = gbuf;
       p.g_rows = H;
       p.sym_partial = symp;
+      // kept features of u_t (forward ran with a feature buffer): kernel A skips the stencils
+      p.feats = feats ? const_cast<T *>(feats) + ((size_t)t * B + b0) * M * img : nullptr;
+      p.feats_vec = feats && W % (16 / (int)sizeof(T)) == 0 && ((uintptr_t)p.feats % 16 == 0) &&
+                    ((uintptr_t)p.lam % 16 == 0);
       int rc = 0;
-      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
+      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(feats ? MODE_BWD_A_KEPT : MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
       if (rc) return rc;
       if (lam_out) {
         AdjParams<T> q;
@@ -1043,11 +1048,23 @@ int pdenet_fd2d_bwd_f32(const float *u, const float *grad_feats, const float *ke
 
 int pdenet_rollout_fwd_f64(const double *u0, const double *kernels, const double *symnet, double *states, int B,
                            int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
-  return rollout_fwd<double>(u0, kernels, symnet, states, B, C, H, W, k, N, L, steps, dt, st);
+  return rollout_fwd<double>(u0, kernels, symnet, states, nullptr, B, C, H, W, k, N, L, steps, dt, st);
 }
 int pdenet_rollout_fwd_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B, int C,
                            int H, int W, int k, int N, int L, int steps, double dt, void *st) {
-  return rollout_fwd<float>(u0, kernels, symnet, states, B, C, H, W, k, N, L, steps, dt, st);
+  return rollout_fwd<float>(u0, kernels, symnet, states, nullptr, B, C, H, W, k, N, L, steps, dt, st);
+}
+int pdenet_rollout_fwd_keep_f64(const double *u0, const double *kernels, const double *symnet, double *states,
+                                double *feats, int B, int C, int H, int W, int k, int N, int L, int steps, double dt,
+                                void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return rollout_fwd<double>(u0, kernels, symnet, states, feats, B, C, H, W, k, N, L, steps, dt, st);
+}
+int pdenet_rollout_fwd_keep_f32(const float *u0, const float *kernels, const float *symnet, float *states,
+                                float *feats, int B, int C, int H, int W, int k, int N, int L, int steps, double dt,
+                                void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return rollout_fwd<float>(u0, kernels, symnet, states, feats, B, C, H, W, k, N, L, steps, dt, st);
 }
 
 size_t pdenet_rollout_bwd_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
@@ -1061,7 +1078,7 @@ int pdenet_rollout_bwd_f64(const double *u0, const double *states, const double 
                            const double *kernels, const double *symnet, double *grad_u0, double *grad_kernels,
                            double *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
                            int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
-  return rollout_bwd<double>(u0, states, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+  return rollout_bwd<double>(u0, states, nullptr, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
                              grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt,
                              st);
 }
@@ -1069,8 +1086,27 @@ int pdenet_rollout_bwd_f32(const float *u0, const float *states, const float *gr
                            const float *kernels, const float *symnet, float *grad_u0, float *grad_kernels,
                            float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B, int C,
                            int H, int W, int k, int N, int L, int steps, double dt, void *st) {
-  return rollout_bwd<float>(u0, states, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels, grad_symnet,
-                            workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st);
+  return rollout_bwd<float>(u0, states, nullptr, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                            grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st);
+}
+int pdenet_rollout_bwd_kept_f64(const double *u0, const double *states, const double *feats,
+                                const double *grad_states, int grad_mode, const double *kernels,
+                                const double *symnet, double *grad_u0, double *grad_kernels, double *grad_symnet,
+                                void *workspace, size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W,
+                                int k, int N, int L, int steps, double dt, void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return rollout_bwd<double>(u0, states, feats, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt,
+                             st);
+}
+int pdenet_rollout_bwd_kept_f32(const float *u0, const float *states, const float *feats, const float *grad_states,
+                                int grad_mode, const float *kernels, const float *symnet, float *grad_u0,
+                                float *grad_kernels, float *grad_symnet, void *workspace, size_t workspace_bytes,
+                                int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
+                                double dt, void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return rollout_bwd<float>(u0, states, feats, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                            grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st);
 }
 
 int pdenet_linear_rollout_fwd_f64(const double *u0, const double *id_kernel, const double *kernels,

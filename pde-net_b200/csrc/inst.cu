@@ -24,7 +24,10 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
   p.n_items = p.B * p.tiles_x * p.tiles_y;
   const int grid = p.n_items < sms ? p.n_items : sms;
-  const size_t smem = Cfg::smem_bytes(p.Psym, MODE == MODE_BWD_A);
+  constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT;
+  if (MODE != MODE_BWD_A_KEPT || Cfg::smem_bytes(p.Psym, true, true) > 227 * 1024)
+    p.feats_vec = 0; // the per-warp strip buffers do not fit: kernel A reads the kept features directly
+  const size_t smem = Cfg::smem_bytes(p.Psym, REV, p.feats_vec != 0);
   auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
@@ -46,6 +49,13 @@ int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms,
       if constexpr (NN * CC + 1 < 16)                                                                            \
         if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, sms, st);                         \
       if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, sms, st);                           \
+    }                                                                                                            \
+    if (mode == MODE_BWD_A_KEPT) {                                                                               \
+      if constexpr (NN * CC + 3 <= 16)                                                                           \
+        if (VL == 16 && p.L == 2) return launch_step_one<T, K, NN, CC, MODE_BWD_A_KEPT, 16, 2>(p, sms, st);      \
+      if constexpr (NN * CC + 1 < 16)                                                                            \
+        if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A_KEPT, 16>(p, sms, st);                    \
+      if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A_KEPT, 32>(p, sms, st);                      \
     }                                                                                                            \
   }
   PDENET_FOR_NC(PDENET_CASE)

@@ -4,7 +4,14 @@
 
 namespace pdenet {
 
-enum StepMode { MODE_FWD = 0, MODE_FEATS = 1, MODE_BWD_A = 2, MODE_LIN_FWD = 3, MODE_LIN_BWD_A = 4 };
+enum StepMode {
+  MODE_FWD = 0,
+  MODE_FEATS = 1,
+  MODE_BWD_A = 2,
+  MODE_LIN_FWD = 3,
+  MODE_LIN_BWD_A = 4,
+  MODE_BWD_A_KEPT = 5 // reverse kernel A reading the features the forward step kept (no stencil recompute)
+};
 
 template <typename T> struct StepParams {
   // input state [B][C][u_rows][W]
@@ -26,6 +33,10 @@ template <typename T> struct StepParams {
   // reverse: derivative adjoints g [B][C*N][g_rows][W]
   T *g;
   int g_rows, g_off;
+  // kept derivative features [B][C*N][H][W] of this step's input state (periodic rollout only):
+  // MODE_FWD stores them when non-NULL, MODE_BWD_A_KEPT reads them instead of recomputing
+  T *feats;
+  int feats_vec; // 1: feats and lam rows may be copied in 16-byte units (W % VEC == 0, bases aligned)
   double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
   int skip_sym_grad;   // 1: ghost-row launch of a slab -- emit g only, contribute no parameter gradient
   T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches

@@ -38,8 +38,14 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static __host__ __device__ constexpr int sym_elems(int Psym) { return round_up(C * Psym, VEC); }
   // per-warp SymNet-gradient accumulators (double, first in shared memory so they stay aligned)
   static __host__ __device__ constexpr int grad_elems(int Psym) { return round_up(C * Psym, 2); }
-  static __host__ size_t smem_bytes(int Psym, bool with_grad) {
-    size_t e = sym_elems(Psym) + 2 * TILE_ELEMS + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
+  // MODE_BWD_A_KEPT: the tile region holds one strip of kept features + adjoints per warp instead
+  static constexpr int KEPT_ROWS = (M + C) * P;           // 32-column rows per warp buffer
+  static constexpr int KEPT_ELEMS = (NT / 32) * KEPT_ROWS * 32;
+  static __host__ __device__ constexpr int tile_region(bool piped) {
+    return (piped && KEPT_ELEMS > 2 * TILE_ELEMS) ? KEPT_ELEMS : 2 * TILE_ELEMS;
+  }
+  static __host__ size_t smem_bytes(int Psym, bool with_grad, bool piped = false) {
+    size_t e = sym_elems(Psym) + tile_region(piped) + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
     return e * sizeof(T) + (with_grad ? (size_t)(NT / 32) * grad_elems(Psym) * sizeof(double) + 64 * sizeof(int) : 0);
   }
 };
@@ -510,7 +516,8 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
-  constexpr bool WITH_GRAD = (MODE == MODE_BWD_A);
+  constexpr bool KEPT = (MODE == MODE_BWD_A_KEPT); // features come from HBM: no tile staging, no block barrier
+  constexpr bool WITH_GRAD = (MODE == MODE_BWD_A || KEPT);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sgrad = reinterpret_cast<double *>(smem_raw); // [NT/32][grad_elems]  (MODE_BWD_A only)
@@ -520,6 +527,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W, L = p.L, Psym = p.Psym;
+  const size_t feat_plane = (size_t)H * W;
 
   // ---- one-time setup: SymNet parameters to shared memory, zeroed gradient accumulators
   if (!LINEAR)
@@ -537,26 +545,59 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   };
 
   int item = blockIdx.x, buf = 0;
-  if (item < p.n_items) stage(item, 0);
-  cp_async_commit();
+  if constexpr (!KEPT) {
+    if (item < p.n_items) stage(item, 0);
+    cp_async_commit();
+  }
 
   const int wx = warp & 1, wy = warp >> 1;
   double *sg = sgrad + warp * Cfg::grad_elems(Psym);
-  T *scratch = tiles + 2 * Cfg::TILE_ELEMS + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (MODE_BWD_A)
-  int *rev_tables = reinterpret_cast<int *>(tiles + 2 * Cfg::TILE_ELEMS + (NT / 32) * TransposeCfg<T>::ELEMS);
+  const bool piped = KEPT && p.feats_vec; // per-warp async-copy pipeline (MODE_BWD_A_KEPT, below)
+  const int region = Cfg::tile_region(piped);
+  T *scratch = tiles + region + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (reverse)
+  int *rev_tables = reinterpret_cast<int *>(tiles + region + (NT / 32) * TransposeCfg<T>::ELEMS);
   constexpr bool REV_FULL = WITH_GRAD && RevFullCfg<M, C, LT>::OK;
   if constexpr (REV_FULL) {
     if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
   }
 
+  // ---- MODE_BWD_A_KEPT: per-warp software pipeline.  Each warp owns a buffer of one strip
+  // ((C*N + C) * P rows of 32 columns: kept features, then the adjoint); while it works on strip q
+  // out of registers, the 16-byte async copies of strip q+1 are in flight.  No block barrier.
+  constexpr int SPW = TH / ((NT / 64) * P); // strips per warp and item
+  constexpr int VEC = Cfg::VEC, UPR = 32 / VEC;
+  T *fbuf = tiles + warp * (Cfg::KEPT_ROWS * 32);
+  auto prefetch = [&](int it, int s) {
+    const int tx = it % p.tiles_x, t2 = it / p.tiles_x, ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+    const int x0 = tx * TW + wx * 32, y0 = ty * TH + (wy * SPW + s) * P;
+    const int cx = (lane % UPR) * VEC, h = lane / UPR;
+    const bool xin = x0 + cx < W;
+    const T *fsrc = p.feats + ((size_t)b * M * H + y0) * W + x0 + cx;
+    const T *lsrc = p.lam + ((size_t)b * C * p.lam_rows + (y0 + p.lam_off)) * W + x0 + cx;
+    constexpr int RPI = 32 / UPR; // rows per iteration (2 in fp64, 4 in fp32)
+#pragma unroll
+    for (int i = 0; i < Cfg::KEPT_ROWS / RPI; ++i) {
+      const int row = i * RPI + h, f = row / P, j = row % P;
+      const bool ok = xin && (y0 + j < H);
+      const T *src = f < M ? fsrc + ((size_t)f * H + j) * W : lsrc + ((size_t)(f - M) * p.lam_rows + j) * W;
+      cp_async_16_zfill(fbuf + row * 32 + cx, ok ? src : p.feats, ok);
+    }
+  };
+  if constexpr (KEPT) {
+    if (piped && item < p.n_items) prefetch(item, 0);
+    cp_async_commit();
+    __syncthreads(); // setup (SymNet parameters, zeroed accumulators, tables) visible to all
+  }
   for (; item < p.n_items; item += gridDim.x) {
     // One barrier per item: this item's tile has landed for every thread and every warp has
     // finished the previous item, so the other buffer can take the next prefetch.
-    cp_async_wait<0>();
-    __syncthreads();
-    const int next = item + gridDim.x;
-    if (next < p.n_items) stage(next, buf ^ 1);
-    cp_async_commit();
+    if constexpr (!KEPT) {
+      cp_async_wait<0>();
+      __syncthreads();
+      const int next = item + gridDim.x;
+      if (next < p.n_items) stage(next, buf ^ 1);
+      cp_async_commit();
+    }
 
     const int tx = item % p.tiles_x, t2 = item / p.tiles_x, ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
     const T *tile = tiles + buf * Cfg::TILE_ELEMS;
@@ -572,18 +613,49 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
       for (int j = 0; j < P; ++j) valid[j] = (x < W) && (y0 + j < H);
       // reverse mode: issue the adjoint loads now so their latency hides behind the stencils
       T lam_raw[WITH_GRAD ? C : 1][P];
+      T d[M][P];
+      if constexpr (KEPT) {
+        if (piped) {
+          cp_async_wait<0>();
+          __syncwarp();
+#pragma unroll
+          for (int f = 0; f < M; ++f)
+#pragma unroll
+            for (int j = 0; j < P; ++j) d[f][j] = fbuf[(f * P + j) * 32 + lane];
+#pragma unroll
+          for (int co = 0; co < C; ++co)
+#pragma unroll
+            for (int j = 0; j < P; ++j) lam_raw[co][j] = fbuf[((M + co) * P + j) * 32 + lane];
+          __syncwarp();
+          // next strip of this warp (possibly in the CTA's next item)
+          const int ns = (s + 1 < SPW) ? s + 1 : 0, nit = (s + 1 < SPW) ? item : item + (int)gridDim.x;
+          if (nit < p.n_items) prefetch(nit, ns);
+          cp_async_commit();
+        }
+      }
       if constexpr (WITH_GRAD) {
+        if (!piped) {
 #pragma unroll
-        for (int co = 0; co < C; ++co) {
-          const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
+          for (int co = 0; co < C; ++co) {
+            const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
 #pragma unroll
-          for (int j = 0; j < P; ++j) lam_raw[co][j] = valid[j] ? lp[(size_t)j * W] : T(0);
+            for (int j = 0; j < P; ++j) lam_raw[co][j] = valid[j] ? lp[(size_t)j * W] : T(0);
+          }
         }
       }
       // ---- derivative features of every channel at the strip's P points (rows a5-a6)
-      T d[M][P];
+      if (KEPT && !piped) {
+        const T *fp = p.feats + ((size_t)b * M * H + y0) * W + x;
+        const size_t plane = (size_t)H * W;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
+        for (int f = 0; f < M; ++f) {
+#pragma unroll
+          for (int j = 0; j < P; ++j) d[f][j] = valid[j] ? fp[(size_t)j * W] : T(0);
+          fp += plane;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < (KEPT ? 0 : C); ++c) {
         const T *ut = tile + (c * SR + row0) * PITCH + col;
         T acc[N][P];
 #pragma unroll
@@ -608,6 +680,20 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
         for (int n = 0; n < N; ++n)
 #pragma unroll
           for (int j = 0; j < P; ++j) d[c * N + n][j] = acc[n][j];
+        if constexpr (MODE == MODE_FWD) {
+          // keep this channel's features for the reverse pass (written once, read once: streaming
+          // stores); issued per channel, while few registers are live, with 32-bit row offsets
+          if (p.feats) {
+            T *fp = p.feats + (((size_t)b * M + c * N) * H + y0) * W + x;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+#pragma unroll
+              for (int j = 0; j < P; ++j)
+                if (valid[j]) __stcs(fp + j * W, acc[n][j]);
+              fp += feat_plane;
+            }
+          }
+        }
       }
 
       if constexpr (MODE == MODE_FEATS) {
@@ -637,7 +723,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
               }
             }
         }
-      } else if constexpr (MODE == MODE_BWD_A) {
+      } else if constexpr (WITH_GRAD && !LINEAR) {
         // ---- SymNet reverse, two points at a time (register budget), rows a7/a11
         if constexpr (REV_FULL) {
           T lamv[C][P];

@@ -144,7 +144,7 @@ class POLYPDE2D(nn.Module):
     """PDE-Net 2.0 model (rows a8-a10): ``forward(init, T)`` = state after ``round(T/dt)`` Euler steps."""
 
     def __init__(self, dt, dx, kernel_size, max_order, constraint, channel_names, hidden_layers=2,
-                 scheme="central", dtype=torch.float64, batch_chunk=0):
+                 scheme="central", dtype=torch.float64, batch_chunk=0, keep_features=None):
         super().__init__()
         if scheme != "central":
             raise NotImplementedError("scheme=%r: only the central scheme is on the B200 hot path" % scheme)
@@ -154,6 +154,7 @@ class POLYPDE2D(nn.Module):
         self.channel_num = len(self.channel_names)
         self.hidden_layers = hidden_layers
         self.batch_chunk = batch_chunk
+        self.keep_features = keep_features  # see ops.rollout: None = keep when they fit the HBM budget
         self.orders = order_list(max_order)
         self._fd_names = []
         for (o0, o1) in self.orders:
@@ -212,7 +213,7 @@ class POLYPDE2D(nn.Module):
     def multistep(self, inputs: torch.Tensor, T: float, all_states: bool = False) -> torch.Tensor:
         steps = max(1, int(round(T / self.dt)))
         return ops.rollout(inputs, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.dt, steps,
-                           last_only=not all_states, batch_chunk=self.batch_chunk)
+                           last_only=not all_states, batch_chunk=self.batch_chunk, keep_features=self.keep_features)
 
     def forward(self, init: torch.Tensor, T: float) -> torch.Tensor:
         return self.multistep(init, T)

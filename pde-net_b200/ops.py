@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import os
+
 import torch
 
 from . import _lib
@@ -145,9 +147,15 @@ def symnet_eval(feat: torch.Tensor, flat: torch.Tensor, L: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ rows a7-a11
+#: HBM budget for keeping the derivative features of a rollout alive between the forward and the
+#: reverse pass (``keep_features=None``): below it the reverse pass reads them back instead of
+#: recomputing the stencils (cfg4: 96 B per grid point and step in fp64).
+FEATURE_CACHE_BYTES = int(float(os.environ.get("PDENET_FEATURE_CACHE_GB", "32")) * 2 ** 30)
+
+
 class _Rollout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk):
+    def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk, keep_features):
         u0 = _req(u0, "u0")
         kernels = _req(kernels, "kernels", u0.dtype)
         symnet = _req(symnet, "symnet", u0.dtype)
@@ -157,9 +165,21 @@ class _Rollout(torch.autograd.Function):
             raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
         states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
-        _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
-            _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
-            _stream()), "pdenet_rollout_fwd")
+        feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
+        if keep_features is None:
+            keep_features = feat_bytes <= FEATURE_CACHE_BYTES
+        keep_features = bool(keep_features) and any(ctx.needs_input_grad[:3])
+        if keep_features:
+            feats = torch.empty(steps, B, Cc * N, H, W, dtype=u0.dtype, device=u0.device)
+            _lib.check(_lib.fn("pdenet_rollout_fwd_keep", u0.dtype)(
+                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), _ptr(feats), B, Cc, H, W, k, N, L, steps,
+                float(dt), _stream()), "pdenet_rollout_fwd_keep")
+        else:
+            feats = None
+            _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
+                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
+                _stream()), "pdenet_rollout_fwd")
+        ctx.feats = feats  # an intermediate, never an output: no reference cycle
         ctx.cfg = (L, float(dt), steps, last_only, batch_chunk)
         if last_only:  # `states` is an intermediate: keep it on ctx (no cycle, it is not an output)
             ctx.save_for_backward(u0, kernels, symnet)
@@ -185,22 +205,33 @@ class _Rollout(torch.autograd.Function):
         gu = torch.empty_like(u0) if need_u else None
         gk = torch.empty_like(kernels) if need_k else None
         gs = torch.empty_like(symnet) if need_s else None
-        _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
-            _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_LAST if last_only else _lib.GRAD_ALL, _ptr(kernels),
-            _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps,
-            dt, _stream()), "pdenet_rollout_bwd")
-        return gu, gk, gs, None, None, None, None, None
+        mode = _lib.GRAD_LAST if last_only else _lib.GRAD_ALL
+        if ctx.feats is not None:
+            _lib.check(_lib.fn("pdenet_rollout_bwd_kept", u0.dtype)(
+                _ptr(u0), _ptr(states), _ptr(ctx.feats), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu),
+                _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
+                "pdenet_rollout_bwd_kept")
+        else:
+            _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
+                _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
+                _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()), "pdenet_rollout_bwd")
+        return gu, gk, gs, None, None, None, None, None, None
 
 
 def rollout(u0: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
-            last_only: bool = False, batch_chunk: int = 0) -> torch.Tensor:
+            last_only: bool = False, batch_chunk: int = 0, keep_features=None) -> torch.Tensor:
     """Fused forward-Euler rollout ``u <- u + dt*SymNet(FD2d(u))`` (rows a5-a10), differentiable
     w.r.t. ``u0``, the scaled ``kernels`` [N,k,k] and the flat ``symnet`` [C,Psym] (row a11).
+
+    ``keep_features``: True keeps the C*N derivative features of every step for the reverse pass
+    (as the reference's autograd does), False recomputes them there, None decides by
+    ``FEATURE_CACHE_BYTES``.  The results are identical bit for bit.
 
     Returns the states after every step ``[steps,B,C,H,W]`` (or only the last one)."""
     if steps < 1:
         raise ValueError("steps must be >= 1")
-    return _Rollout.apply(u0, kernels, symnet, int(L), float(dt), int(steps), bool(last_only), int(batch_chunk))
+    return _Rollout.apply(u0, kernels, symnet, int(L), float(dt), int(steps), bool(last_only), int(batch_chunk),
+                          keep_features)
 
 
 # ------------------------------------------------------------------------------ row a12

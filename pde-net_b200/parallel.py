@@ -235,6 +235,21 @@ def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u
     return final, bufs.lam[cur][:, :, h:h + Hs].contiguous(), gk, gs
 
 
+def chunked_fwd_bwd(model, u0: torch.Tensor, T: float, loss_scale: float, chunk: int) -> torch.Tensor:
+    """Forward + reverse rollout over a DEVICE-resident batch, ``chunk`` trajectories at a time
+    (trajectories are independent; parameter gradients accumulate in ``.grad``).  Bounding the
+    live set to one chunk is what lets the rollout keep its derivative features for the reverse
+    pass (``ops.rollout(keep_features=...)``: 96 B per grid point and step at cfg4) instead of
+    recomputing the stencils.  Loss as in :func:`streamed_fwd_bwd`."""
+    total = torch.zeros((), dtype=u0.dtype, device=u0.device)
+    for b0 in range(0, u0.shape[0], chunk):
+        out = model(u0[b0:b0 + chunk], T)
+        loss = out.square().sum() * loss_scale
+        loss.backward()
+        total = total + loss.detach()
+    return total
+
+
 def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, chunk: int,
                      bufs=None, copy_stream=None):
     """End-to-end pass over a batch that lives in PINNED HOST memory: trajectories are independent,

@@ -151,8 +151,9 @@ EDGE_CASES = [
 
 
 @pytest.mark.parametrize("case", EDGE_CASES)
-def test_rollout_parity_edge_shapes(P, cuda_device, case):
-    got, ref = run_both(P, cuda_device, case, torch.float64, True)
+@pytest.mark.parametrize("keep", [False, True])
+def test_rollout_parity_edge_shapes(P, cuda_device, case, keep):
+    got, ref = run_both(P, cuda_device, case, torch.float64, True, keep=keep)
     steps = case[7]
     for n, a, b in zip(["states", "grad_u0", "grad_kernels", "grad_symnet"], got, ref):
         assert rel(a, b) < TOL[torch.float64] * max(1, steps), (n, rel(a, b))
@@ -174,7 +175,8 @@ def test_unsupported_combinations_are_refused(P, cuda_device):
                   torch.zeros(2, 69, dtype=torch.float64, device=dev), 2, 1e-2, 1)
 
 
-def run_both(P, dev, case, dtype, grad_all, batch_chunk=0):
+def run_both(P, dev, case, dtype, grad_all, batch_chunk=0, keep=None):
+    """keep: reverse pass reads the features the forward kept (True) or recomputes them (False)."""
     k, max_order, C, L, B, H, W, steps, dx, dt = case
     orders, M, scales, sym = make_model(k, max_order, C, L, dx, 7)
     Ks = O.scaled_kernels(M, scales)
@@ -193,10 +195,10 @@ def run_both(P, dev, case, dtype, grad_all, batch_chunk=0):
     sd = sym.to(dev, dtype).requires_grad_(True)
     wd = w.to(dev, dtype)
     if grad_all:
-        st = P.rollout(ud, Kd, sd, L, dt, steps, batch_chunk=batch_chunk)
+        st = P.rollout(ud, Kd, sd, L, dt, steps, batch_chunk=batch_chunk, keep_features=keep)
         (st * wd).sum().backward()
     else:
-        last = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True, batch_chunk=batch_chunk)
+        last = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True, batch_chunk=batch_chunk, keep_features=keep)
         (last * wd[-1]).sum().backward()
         st = last[None]
         st_ref = st_ref[-1:]
@@ -205,8 +207,9 @@ def run_both(P, dev, case, dtype, grad_all, batch_chunk=0):
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("grad_all", [False, True])
-def test_rollout_parity_fp64(P, cuda_device, case, grad_all):
-    got, ref = run_both(P, cuda_device, case, torch.float64, grad_all)
+@pytest.mark.parametrize("keep", [False, True])
+def test_rollout_parity_fp64(P, cuda_device, case, grad_all, keep):
+    got, ref = run_both(P, cuda_device, case, torch.float64, grad_all, keep=keep)
     steps = case[7]
     names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
     for n, a, b in zip(names, got, ref):
@@ -228,10 +231,11 @@ def oracle_fp32(case):
 
 
 @pytest.mark.parametrize("case", CASES[:5])
-def test_rollout_parity_fp32(P, cuda_device, case):
+@pytest.mark.parametrize("keep", [False, True])
+def test_rollout_parity_fp32(P, cuda_device, case, keep):
     """fp32: within 1e-5 relative per step of the fp64 oracle, or -- where the 1/dx^2-scaled taps
     make fp32 itself less accurate than that -- no worse than 3x the fp32 oracle's own error."""
-    got, ref = run_both(P, cuda_device, case, torch.float32, True)
+    got, ref = run_both(P, cuda_device, case, torch.float32, True, keep=keep)
     cpu32 = oracle_fp32(case)
     steps = case[7]
     names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
@@ -240,11 +244,23 @@ def test_rollout_parity_fp32(P, cuda_device, case):
         assert rel(a, b) < bound, (n, rel(a, b), bound)
 
 
-def test_batch_chunk_and_determinism(P, cuda_device):
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[6], EDGE_CASES[7]])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_kept_features_equal_recomputed_bitwise(P, cuda_device, case, dtype):
+    """The feature-keeping rollout (pdenet_rollout_fwd_keep / bwd_kept) stores exactly the values
+    the plain reverse pass recomputes, so states and all gradients agree bit for bit."""
+    a, _ = run_both(P, cuda_device, case, dtype, True, batch_chunk=2, keep=True)
+    b, _ = run_both(P, cuda_device, case, dtype, True, batch_chunk=2, keep=False)
+    for n, x, y in zip(["states", "grad_u0", "grad_kernels", "grad_symnet"], a, b):
+        assert torch.equal(x, y), n
+
+
+@pytest.mark.parametrize("keep", [False, True])
+def test_batch_chunk_and_determinism(P, cuda_device, keep):
     case = (5, 2, 2, 2, 5, 37, 53, 3, 0.2, 1e-2)
-    a, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0)
-    b, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0)
-    c, ref = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=2)
+    a, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0, keep=keep)
+    b, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=0, keep=keep)
+    c, ref = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=2, keep=keep)
     for x, y in zip(a, b):
         assert torch.equal(x, y)  # bit-identical repeat
     for x, y in zip(c, ref):
