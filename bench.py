@@ -306,7 +306,10 @@ def run_ours(args):
     # operand-pattern probes: register-bank limit of a 3-vector-operand DFMA
     fma_probe = {"loop_invariant_operands": fma_peak / 1e12,
                  "three_distinct_vector_operands": ops.fma_peak(dtype, 2048, 1) / 1e12,
-                 "one_operand_shared_by_4": ops.fma_peak(dtype, 2048, 2) / 1e12}
+                 "one_operand_shared_by_4": ops.fma_peak(dtype, 2048, 2) / 1e12,
+                 # the filter-gradient kernel's own register pattern (49 accumulators, g shared by 7
+                 # FMAs, window rows from shared memory): the ceiling of kernel B2
+                 "filter_gradient_pattern": ops.fma_peak(dtype, 512, 3) / 1e12}
 
     for _ in range(max(args.warmup, 3)):
         one_pass(u0)

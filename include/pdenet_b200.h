@@ -249,7 +249,10 @@ PDENET_API int pdenet_profile_read(double *ms_by_kind, long long *launches_by_ki
 PDENET_API int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, void *stream);
 /* Register-operand probes of the FMA pipe: variant 0 = x = fma(x, a, b) with
  * loop-invariant a, b (what pdenet_fma_peak runs); 1 = three distinct register operands per FMA,
- * none shared with the neighbouring FMAs; 2 = one operand shared by 4 consecutive FMAs. */
+ * none shared with the neighbouring FMAs; 2 = one operand shared by 4 consecutive FMAs;
+ * 3 / 4 = the filter-gradient kernel's register pattern (49 accumulators per thread, one
+ * multiplicand shared by 7 consecutive FMAs, window rows re-read from shared memory) with two / one
+ * grid columns per lane. */
 PDENET_API int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream);
 
 #ifdef __cplusplus

@@ -962,6 +962,52 @@ template <typename T, int VARIANT> __global__ void __launch_bounds__(256) fma_pr
   if (s == (T)123456789) out[0] = s;
 }
 
+// operand pattern of the filter-gradient kernel: 49 accumulators per thread, the g value shared by
+// 7 consecutive FMAs, the window row re-read from shared memory per row.  VEC = columns per lane
+// (2: every accumulator meets two adjacent window registers; 1: exactly one).
+template <typename T, int VEC> __global__ void __launch_bounds__(192, 2) fgrad_probe_kernel(T *out, int iters) {
+  constexpr int K = 7, RW = 16 / VEC;
+  __shared__ T sm[16 * 48];
+  for (int i = threadIdx.x; i < 16 * 48; i += blockDim.x) sm[i] = (T)0.999 + (T)i * (T)1e-6;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  T acc[K * K], gc[RW][VEC];
+#pragma unroll
+  for (int e = 0; e < K * K; ++e) acc[e] = T(0);
+#pragma unroll
+  for (int j = 0; j < RW; ++j)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) gc[j][i] = (T)1e-3 * (T)(threadIdx.x + j + 3 * i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rho = 0; rho < RW + K - 1; ++rho) {
+      T row[VEC + K - 1];
+#pragma unroll
+      for (int x = 0; x < VEC + K - 1; ++x) row[x] = sm[((rho + it) & 15) * 48 + ((lane * VEC + x) & 47)];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+          const int j = rho - a;
+          if (j >= 0 && j < RW) {
+#pragma unroll
+            for (int bb = 0; bb < K; ++bb) acc[a * K + bb] = fma_(gc[j][i], row[i + bb], acc[a * K + bb]);
+          }
+        }
+    }
+    if (it == iters + 1) { // never true: keeps gc live as variables
+#pragma unroll
+      for (int j = 0; j < RW; ++j)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) gc[j][i] += acc[j];
+    }
+  }
+  T s = T(0);
+#pragma unroll
+  for (int e = 0; e < K * K; ++e) s += acc[e];
+  if (s == (T)123456789) out[0] = s;
+}
+
 } // namespace pdenet
 
 using namespace pdenet;
@@ -1270,7 +1316,7 @@ int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, 
 }
 
 int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream) {
-  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out || variant < 0 || variant > 2)
+  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out || variant < 0 || variant > 4)
     return PDENET_E_BADARG;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
@@ -1280,23 +1326,27 @@ int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, f
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int grid = sms * 8, block = 256;
+  const int grid = sms * 8, block = variant >= 3 ? 192 : 256;
   for (int rep = 0; rep < 2; ++rep) { // first pass warms up
     cudaEventRecord(e0, st);
     if (elem_size == 8) {
       if (variant == 0) fma_peak_kernel<double><<<grid, block, 0, st>>>((double *)scratch, iters, 0.999, 1e-3);
       if (variant == 1) fma_probe_kernel<double, 1><<<grid, block, 0, st>>>((double *)scratch, iters);
       if (variant == 2) fma_probe_kernel<double, 2><<<grid, block, 0, st>>>((double *)scratch, iters);
+      if (variant == 3) fgrad_probe_kernel<double, 2><<<grid, block, 0, st>>>((double *)scratch, iters);
+      if (variant == 4) fgrad_probe_kernel<double, 1><<<grid, block, 0, st>>>((double *)scratch, iters);
     } else {
       if (variant == 0) fma_peak_kernel<float><<<grid, block, 0, st>>>((float *)scratch, iters, 0.999f, 1e-3f);
       if (variant == 1) fma_probe_kernel<float, 1><<<grid, block, 0, st>>>((float *)scratch, iters);
       if (variant == 2) fma_probe_kernel<float, 2><<<grid, block, 0, st>>>((float *)scratch, iters);
+      if (variant == 3) fgrad_probe_kernel<float, 2><<<grid, block, 0, st>>>((float *)scratch, iters);
+      if (variant == 4) fgrad_probe_kernel<float, 1><<<grid, block, 0, st>>>((float *)scratch, iters);
     }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
   }
   cudaEventElapsedTime(ms_out, e0, e1);
-  *flops_out = 2.0 * 16 * 8 * (double)iters * (double)grid * block;
+  *flops_out = 2.0 * (variant >= 3 ? 784 : 16 * 8) * (double)iters * (double)grid * block;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(scratch);
