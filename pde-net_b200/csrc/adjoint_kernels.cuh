@@ -148,22 +148,29 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
       // ---- B1: data gradient (correlation of g_n with the flipped filter)
       {
         const T *wn0 = cw + n * KK; // this filter's taps; flipped index below = transposed correlation
+        // window rows in pairs: each tap fetched into a uniform register feeds 2*VEC FMAs
+        static_assert((RW + K - 1) % 2 == 0, "window rows are processed in pairs");
 #pragma unroll
-        for (int rho = 0; rho < RW + K - 1; ++rho) {
-          const T *wn = wn0 + p.zz[rho];
-          T row[NV * VEC];
+        for (int rp = 0; rp < (RW + K - 1) / 2; ++rp) {
+          const T *wn = wn0 + p.zz[rp];
+          T row[2][NV * VEC];
 #pragma unroll
-          for (int v = 0; v < NV; ++v)
-            ld_vec(gs + rho * PITCH + v * VEC, &row[v * VEC]);
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) ld_vec(gs + (2 * rp + h) * PITCH + v * VEC, &row[h][v * VEC]);
           // tap column outermost: consecutive FMAs hit different accumulators (no dependent chains)
 #pragma unroll
           for (int bb = 0; bb < K; ++bb)
 #pragma unroll
             for (int a = 0; a < K; ++a) {
-              const int j = rho - a;
-              if (j >= 0 && j < RW) {
+              const T w = wn[KK - 1 - (a * K + bb)];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) lacc[j][i] = fma_(row[i + bb], wn[KK - 1 - (a * K + bb)], lacc[j][i]);
+              for (int h = 0; h < 2; ++h) {
+                const int j = 2 * rp + h - a;
+                if (j >= 0 && j < RW) {
+#pragma unroll
+                  for (int i = 0; i < VEC; ++i) lacc[j][i] = fma_(row[h][i + bb], w, lacc[j][i]);
+                }
               }
             }
         }
