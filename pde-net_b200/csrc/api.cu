@@ -683,8 +683,6 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
       p.sym_partial = symp;
       // kept features of u_t (forward ran with a feature buffer): kernel A skips the stencils
       p.feats = feats ? const_cast<T *>(feats) + ((size_t)t * B + b0) * M * img : nullptr;
-      p.feats_vec = feats && W % (16 / (int)sizeof(T)) == 0 && ((uintptr_t)p.feats % 16 == 0) &&
-                    ((uintptr_t)p.lam % 16 == 0);
       int rc = 0;
       PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(feats ? MODE_BWD_A_KEPT : MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
       if (rc) return rc;

@@ -25,9 +25,7 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.n_items = p.B * p.tiles_x * p.tiles_y;
   const int grid = p.n_items < sms ? p.n_items : sms;
   constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT;
-  if (MODE != MODE_BWD_A_KEPT || Cfg::smem_bytes(p.Psym, true, true) > 227 * 1024)
-    p.feats_vec = 0; // the per-warp strip buffers do not fit: kernel A reads the kept features directly
-  const size_t smem = Cfg::smem_bytes(p.Psym, REV, p.feats_vec != 0);
+  const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);
   auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);

@@ -36,7 +36,6 @@ template <typename T> struct StepParams {
   // kept derivative features [B][C*N][H][W] of this step's input state (periodic rollout only):
   // MODE_FWD stores them when non-NULL, MODE_BWD_A_KEPT reads them instead of recomputing
   T *feats;
-  int feats_vec; // 1: feats and lam rows may be copied in 16-byte units (W % VEC == 0, bases aligned)
   double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
   int skip_sym_grad;   // 1: ghost-row launch of a slab -- emit g only, contribute no parameter gradient
   T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches

@@ -38,14 +38,11 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   static __host__ __device__ constexpr int sym_elems(int Psym) { return round_up(C * Psym, VEC); }
   // per-warp SymNet-gradient accumulators (double, first in shared memory so they stay aligned)
   static __host__ __device__ constexpr int grad_elems(int Psym) { return round_up(C * Psym, 2); }
-  // MODE_BWD_A_KEPT: the tile region holds one strip of kept features + adjoints per warp instead
-  static constexpr int KEPT_ROWS = (M + C) * P;           // 32-column rows per warp buffer
-  static constexpr int KEPT_ELEMS = (NT / 32) * KEPT_ROWS * 32;
-  static __host__ __device__ constexpr int tile_region(bool piped) {
-    return (piped && KEPT_ELEMS > 2 * TILE_ELEMS) ? KEPT_ELEMS : 2 * TILE_ELEMS;
-  }
-  static __host__ size_t smem_bytes(int Psym, bool with_grad, bool piped = false) {
-    size_t e = sym_elems(Psym) + tile_region(piped) + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
+  // MODE_BWD_A_KEPT stages no tiles (the shared memory it leaves free stays L1 cache)
+  static constexpr int KEPT_ROWS = (M + C) * P; // rows of 32 columns one warp reads per strip: features + adjoint
+  static __host__ __device__ constexpr int tile_region(bool kept) { return kept ? 0 : 2 * TILE_ELEMS; }
+  static __host__ size_t smem_bytes(int Psym, bool with_grad, bool kept = false) {
+    size_t e = sym_elems(Psym) + tile_region(kept) + (with_grad ? (NT / 32) * TransposeCfg<T>::ELEMS : 0);
     return e * sizeof(T) + (with_grad ? (size_t)(NT / 32) * grad_elems(Psym) * sizeof(double) + 64 * sizeof(int) : 0);
   }
 };
@@ -552,8 +549,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 
   const int wx = warp & 1, wy = warp >> 1;
   double *sg = sgrad + warp * Cfg::grad_elems(Psym);
-  const bool piped = KEPT && p.feats_vec; // per-warp async-copy pipeline (MODE_BWD_A_KEPT, below)
-  const int region = Cfg::tile_region(piped);
+  constexpr int region = Cfg::tile_region(KEPT);
   T *scratch = tiles + region + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (reverse)
   int *rev_tables = reinterpret_cast<int *>(tiles + region + (NT / 32) * TransposeCfg<T>::ELEMS);
   constexpr bool REV_FULL = WITH_GRAD && RevFullCfg<M, C, LT>::OK;
@@ -561,33 +557,8 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
   }
 
-  // ---- MODE_BWD_A_KEPT: per-warp software pipeline.  Each warp owns a buffer of one strip
-  // ((C*N + C) * P rows of 32 columns: kept features, then the adjoint); while it works on strip q
-  // out of registers, the 16-byte async copies of strip q+1 are in flight.  No block barrier.
   constexpr int SPW = TH / ((NT / 64) * P); // strips per warp and item
-  constexpr int VEC = Cfg::VEC, UPR = 32 / VEC;
-  T *fbuf = tiles + warp * (Cfg::KEPT_ROWS * 32);
-  auto prefetch = [&](int it, int s) {
-    const int tx = it % p.tiles_x, t2 = it / p.tiles_x, ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
-    const int x0 = tx * TW + wx * 32, y0 = ty * TH + (wy * SPW + s) * P;
-    const int cx = (lane % UPR) * VEC, h = lane / UPR;
-    const bool xin = x0 + cx < W;
-    const T *fsrc = p.feats + ((size_t)b * M * H + y0) * W + x0 + cx;
-    const T *lsrc = p.lam + ((size_t)b * C * p.lam_rows + (y0 + p.lam_off)) * W + x0 + cx;
-    constexpr int RPI = 32 / UPR; // rows per iteration (2 in fp64, 4 in fp32)
-#pragma unroll
-    for (int i = 0; i < Cfg::KEPT_ROWS / RPI; ++i) {
-      const int row = i * RPI + h, f = row / P, j = row % P;
-      const bool ok = xin && (y0 + j < H);
-      const T *src = f < M ? fsrc + ((size_t)f * H + j) * W : lsrc + ((size_t)(f - M) * p.lam_rows + j) * W;
-      cp_async_16_zfill(fbuf + row * 32 + cx, ok ? src : p.feats, ok);
-    }
-  };
-  if constexpr (KEPT) {
-    if (piped && item < p.n_items) prefetch(item, 0);
-    cp_async_commit();
-    __syncthreads(); // setup (SymNet parameters, zeroed accumulators, tables) visible to all
-  }
+  if constexpr (KEPT) __syncthreads();      // setup (SymNet parameters, zeroed accumulators, tables) visible to all
   for (; item < p.n_items; item += gridDim.x) {
     // One barrier per item: this item's tile has landed for every thread and every warp has
     // finished the previous item, so the other buffer can take the next prefetch.
@@ -614,37 +585,16 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
       // reverse mode: issue the adjoint loads now so their latency hides behind the stencils
       T lam_raw[WITH_GRAD ? C : 1][P];
       T d[M][P];
-      if constexpr (KEPT) {
-        if (piped) {
-          cp_async_wait<0>();
-          __syncwarp();
-#pragma unroll
-          for (int f = 0; f < M; ++f)
-#pragma unroll
-            for (int j = 0; j < P; ++j) d[f][j] = fbuf[(f * P + j) * 32 + lane];
-#pragma unroll
-          for (int co = 0; co < C; ++co)
-#pragma unroll
-            for (int j = 0; j < P; ++j) lam_raw[co][j] = fbuf[((M + co) * P + j) * 32 + lane];
-          __syncwarp();
-          // next strip of this warp (possibly in the CTA's next item)
-          const int ns = (s + 1 < SPW) ? s + 1 : 0, nit = (s + 1 < SPW) ? item : item + (int)gridDim.x;
-          if (nit < p.n_items) prefetch(nit, ns);
-          cp_async_commit();
-        }
-      }
       if constexpr (WITH_GRAD) {
-        if (!piped) {
 #pragma unroll
-          for (int co = 0; co < C; ++co) {
-            const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
+        for (int co = 0; co < C; ++co) {
+          const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
 #pragma unroll
-            for (int j = 0; j < P; ++j) lam_raw[co][j] = valid[j] ? lp[(size_t)j * W] : T(0);
-          }
+          for (int j = 0; j < P; ++j) lam_raw[co][j] = valid[j] ? lp[(size_t)j * W] : T(0);
         }
       }
       // ---- derivative features of every channel at the strip's P points (rows a5-a6)
-      if (KEPT && !piped) {
+      if constexpr (KEPT) {
         const T *fp = p.feats + ((size_t)b * M * H + y0) * W + x;
         const size_t plane = (size_t)H * W;
 #pragma unroll
@@ -652,6 +602,29 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 #pragma unroll
           for (int j = 0; j < P; ++j) d[f][j] = valid[j] ? fp[(size_t)j * W] : T(0);
           fp += plane;
+        }
+        // No tile, no stencils: the strip's features come straight from HBM (coalesced 256-byte
+        // rows).  While this strip computes, the lines of the warp's NEXT strip (possibly in the
+        // CTA's next item) are pulled into L1, so its loads hit the cache.
+        {
+          const int ns = (s + 1 < SPW) ? s + 1 : 0, nit = (s + 1 < SPW) ? item : item + (int)gridDim.x;
+          if (nit < p.n_items) {
+            const int ntx = nit % p.tiles_x, nt2 = nit / p.tiles_x, nty = nt2 % p.tiles_y, nb = nt2 / p.tiles_y;
+            const int nx0 = ntx * TW + wx * 32, ny0 = nty * TH + (wy * SPW + ns) * P;
+            constexpr int LPR = 32 * (int)sizeof(T) / 128; // 128-byte lines per 32-column row
+            constexpr int NL = Cfg::KEPT_ROWS * LPR;
+#pragma unroll
+            for (int q = 0; q < (NL + 31) / 32; ++q) {
+              const int line = q * 32 + lane, row = line / LPR, hx = (line % LPR) * (128 / (int)sizeof(T));
+              const int f = row / P, j = row % P;
+              if (line < NL && ny0 + j < H && nx0 + hx < W) {
+                const T *src = f < M ? p.feats + (((size_t)nb * M + f) * H + ny0 + j) * W + nx0 + hx
+                                     : p.lam + (((size_t)nb * C + (f - M)) * p.lam_rows + ny0 + j + p.lam_off) * W +
+                                           nx0 + hx;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+              }
+            }
+          }
         }
       }
 #pragma unroll
@@ -810,7 +783,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     }
     buf ^= 1;
   }
-  cp_async_wait<0>();
+  if constexpr (!KEPT) cp_async_wait<0>();
 
   if constexpr (WITH_GRAD) {
     __syncthreads();
