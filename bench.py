@@ -172,10 +172,20 @@ def oracle_pass(sample, threads):
 CPU_SAMPLE = dict(B=8, H=1024, W=1024, blocks=4)
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(threads):
     oracle_pass(dict(B=1, H=128, W=128, blocks=1), threads)  # warm-up (thread pool, allocator)
     v, dt = oracle_pass(CPU_SAMPLE, threads)
-    return {"value": v, "unit": "grid-point-steps/s", "cores": threads, "kind": "port",
+    return {"value": v, "unit": "grid-point-steps/s", "cores": threads, "cpu": cpu_model(), "kind": "port",
             "sample": "oracle fwd+bwd, B=%(B)d %(H)dx%(W)d, %(blocks)d dt-blocks, fp64, same model" % CPU_SAMPLE
                       + " (%.1f s)" % dt}
 
@@ -200,8 +210,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": CFG["workload"], "note": "reference mount has no source; CPU oracle (eager "
                        "PyTorch restatement) timed on a bounded sample, throughput is per grid-point-step"},
-            "cpu_baseline": {"value": value, "unit": "grid-point-steps/s", "cores": threads, "kind": "port",
-                             "sample": "oracle fwd+bwd, B=%(B)d %(H)dx%(W)d, %(blocks)d dt-blocks per step"
+            "cpu_baseline": {"value": value, "unit": "grid-point-steps/s", "cores": threads, "cpu": cpu_model(),
+                             "kind": "port", "sample": "oracle fwd+bwd, B=%(B)d %(H)dx%(W)d, %(blocks)d dt-blocks per step"
                                        % CPU_SAMPLE},
             "e2e": {"value": value, "unit": "grid-point-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},

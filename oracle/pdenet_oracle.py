@@ -222,3 +222,25 @@ def linear_rollout(u0, K0, Ks, coe, dt, steps: int):
         u = linear_step(u, K0, Ks, coe, dt)
         states.append(u)
     return states
+
+
+# ----------------------------------------------------------------------------- f-3
+def huber_l1(p: torch.Tensor, threshold: float) -> torch.Tensor:
+    """Huber-smoothed L1 norm used by the training loss's sparsity terms (upstream
+    ``setups.py`` [RECALL]): ``|p| - threshold/2`` outside ``[-threshold, threshold]``,
+    ``p^2 / (2 threshold)`` inside."""
+    a = p.abs()
+    return torch.where(a >= threshold, a - threshold / 2, p * p / (2 * threshold)).sum()
+
+
+def training_loss(u0, moments, scales, pinned, symnet, L, dt, observed, block_weights=None, sparsity=0.0,
+                  momentsparsity=0.0, symnet_threshold=1e-3, moment_threshold=1e-2):
+    """Loss of one optimiser evaluation (upstream ``train.py`` closure [RECALL]):
+    ``sum_t w_t mean((u_t - obs_t)^2) + blocks * (sparsity * H(symnet) + momentsparsity * H(free moments))``."""
+    blocks = observed.shape[0]
+    states = torch.stack(rollout(u0, scaled_kernels(moments, scales), symnet, L, dt, blocks))
+    w = [1.0] * blocks if block_weights is None else list(block_weights)
+    loss = sum(w[t] * ((states[t] - observed[t]) ** 2).mean() for t in range(blocks))
+    loss = loss + blocks * sparsity * huber_l1(symnet, symnet_threshold)
+    loss = loss + blocks * momentsparsity * huber_l1(moments[~pinned], moment_threshold)
+    return loss

@@ -4,12 +4,12 @@ Importable as ``pdenet_b200`` (see the shim ``pdenet_b200.py`` at the repository
 directory itself is called ``pde-net_b200``).  Hand-written CUDA for sm_100a behind a C-ABI
 (``include/pdenet_b200.h``), bound with ctypes and wired into torch.autograd.
 """
-from . import _lib, ops, optim, parallel
+from . import _lib, losses, ops, optim, parallel
 from .optim import FlatParams
 from .modules import FD2d, K2M, LagrangeInterpFixInputs2d, M2K, POLYPDE2D, VariantCoeLinear2d, order_list, poly
 from .ops import (fd2d, fd2d_features, fma_peak, k2m, linear_rollout, m2k, mse_loss, rollout, slab_step, symnet_eval,
                   symnet_param_count)
 
-__all__ = ["LagrangeInterpFixInputs2d", "FlatParams", "optim", "FD2d", "K2M", "M2K", "POLYPDE2D", "VariantCoeLinear2d", "order_list", "poly", "fd2d",
+__all__ = ["losses", "LagrangeInterpFixInputs2d", "FlatParams", "optim", "FD2d", "K2M", "M2K", "POLYPDE2D", "VariantCoeLinear2d", "order_list", "poly", "fd2d",
            "fd2d_features", "fma_peak", "k2m", "linear_rollout", "m2k", "mse_loss", "rollout", "slab_step", "symnet_eval",
            "symnet_param_count", "ops", "parallel"]

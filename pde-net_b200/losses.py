@@ -1,0 +1,71 @@
+"""Training-loss closure around the fused rollout.
+
+Upstream's ``train.py`` / ``setups.py`` [RECALL -- the mounted reference holds no source, so the
+exact constants are the caller's] build the loss of one L-BFGS evaluation as
+
+    loss = data_loss + stepnum * (sparsity * symnet_loss + momentsparsity * moment_loss)
+
+with ``data_loss`` the mean-square misfit of the rolled-out states against the observed ones at
+every supervised dt-block, ``symnet_loss`` a Huber-smoothed L1 norm of all SymNet parameters
+(``expr_params``) and ``moment_loss`` the same penalty on the free (non-pinned) moment entries of
+the finite-difference bank (``diff_params``).  Here the data term and its gradient seed come out of
+one fused pass (``ops.mse_loss`` -> ``pdenet_mse_seed_*``); the regularisers touch a few hundred
+scalars and are plain device tensor ops.  Nothing runs on the host, so a whole evaluation
+(forward, loss, reverse) can be captured in one CUDA graph."""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+def huber_l1(params: Iterable[torch.Tensor], threshold: float) -> torch.Tensor:
+    """``sum_i h(p_i)`` with ``h(p) = |p| - threshold/2`` for ``|p| >= threshold`` and
+    ``p**2 / (2*threshold)`` below: an L1 norm smoothed at the origin (value and slope continuous
+    at ``|p| = threshold``)."""
+    total = None
+    for p in params:
+        h = _huber(p, threshold).sum()
+        total = h if total is None else total + h
+    if total is None:
+        raise ValueError("huber_l1: no parameters")
+    return total
+
+
+def _huber(p: torch.Tensor, threshold: float) -> torch.Tensor:
+    a = p.abs()
+    return torch.where(a >= threshold, a - 0.5 * threshold, p * p * (0.5 / threshold))
+
+
+def symnet_sparsity(model, threshold: float = 1e-3) -> torch.Tensor:
+    """Smoothed L1 norm of every SymNet weight and bias (``model.expr_params()``)."""
+    return huber_l1(model.expr_params(), threshold)
+
+
+def moment_sparsity(model, threshold: float = 1e-2) -> torch.Tensor:
+    """Smoothed L1 norm of the FREE moment entries of the filter bank: pinned entries (sum-rule
+    constraint) carry no penalty and no gradient."""
+    total = None
+    for fd in model.fds if not hasattr(model, "id") else [model.id] + list(model.fds):
+        h = _huber(fd.moment, threshold).masked_fill(fd._pinned, 0).sum()  # static mask: no host sync
+        total = h if total is None else total + h
+    return total
+
+
+def training_loss(model, u0: torch.Tensor, observed: torch.Tensor, block_weights: Optional[Sequence[float]] = None,
+                  sparsity: float = 0.0, momentsparsity: float = 0.0, symnet_threshold: float = 1e-3,
+                  moment_threshold: float = 1e-2) -> torch.Tensor:
+    """One evaluation of the training objective: roll ``u0`` [B,C,H,W] out over
+    ``observed.shape[0]`` dt-blocks, compare every block with ``observed`` [blocks,B,C,H,W]
+    (weights ``block_weights``, default 1 each) and add the two sparsity terms scaled by the number
+    of blocks.  Returns the scalar loss with the autograd graph attached."""
+    blocks = observed.shape[0]
+    states = model.multistep(u0, blocks * model.dt, all_states=True)
+    loss = ops.mse_loss(states, observed, block_weights)
+    if sparsity:
+        loss = loss + (blocks * sparsity) * symnet_sparsity(model, symnet_threshold)
+    if momentsparsity:
+        loss = loss + (blocks * momentsparsity) * moment_sparsity(model, moment_threshold)
+    return loss

@@ -588,6 +588,44 @@ def test_mse_loss_seed(P, cuda_device, dtype):
     assert loss2.item() == loss.item()  # deterministic
 
 
+def test_training_loss_closure_matches_oracle(P, cuda_device):
+    """8f-3: data term + Huber-L1 sparsity of the SymNet and of the free moments, value and all
+    parameter gradients against the oracle's closure."""
+    dev = cuda_device
+    k, max_order, C, L, B, H, W, blocks, dx, dt = 5, 2, 2, 2, 3, 24, 40, 3, 0.3, 1e-2
+    orders, M, scales, sym = make_model(k, max_order, C, L, dx, 21)
+    sym = sym * 0.02      # entries on both sides of the Huber threshold
+    pinned = torch.stack([O.pinned_mask(k, o, "moment") for o in orders])
+    u0 = smooth_field(B, C, H, W, 22)
+    with torch.no_grad():
+        obs = torch.stack(O.rollout(u0, O.scaled_kernels(M, scales), sym * 1.1, L, dt, blocks))
+    wts = [1.0, 0.5, 2.0]
+    Mc, sc = M.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    ref = O.training_loss(u0, Mc, scales, pinned, sc, L, dt, obs, wts, sparsity=5e-3, momentsparsity=1e-3,
+                          symnet_threshold=1e-3, moment_threshold=1e-2)
+    ref.backward()
+    Mc.grad[pinned] = 0
+
+    model = P.POLYPDE2D(dt, dx, k, max_order, "moment", "u,v", hidden_layers=L).to(dev)
+    with torch.no_grad():
+        for fd, m in zip(model.fds, M):
+            fd.moment.copy_(m)
+        for c, pl in enumerate(model.polys):
+            o = 0
+            for prm in pl.parameters():
+                prm.copy_(sym[c, o:o + prm.numel()].reshape(prm.shape))
+                o += prm.numel()
+    loss = P.losses.training_loss(model, u0.to(dev), obs.to(dev), wts, sparsity=5e-3, momentsparsity=1e-3,
+                                  symnet_threshold=1e-3, moment_threshold=1e-2)
+    loss.backward()
+    model.diff_grad_proj()
+    assert abs(loss.item() - ref.item()) < 1e-10 * abs(ref.item())
+    gM = torch.stack([fd.moment.grad for fd in model.fds])
+    assert rel(gM, Mc.grad) < 1e-9
+    gs = torch.stack([torch.cat([prm.grad.reshape(-1) for prm in pl.parameters()]) for pl in model.polys])
+    assert rel(gs, sc.grad) < 1e-9
+
+
 def test_lbfgs_training_loop_reduces_loss(P, cuda_device):
     """The reference-style driver (SciPy L-BFGS over FlatParams, loss = fused MSE seed, projection
     hooks) runs on the CUDA path and fits synthetic Burgers data (examples/learn_burgers_lbfgs.py)."""
