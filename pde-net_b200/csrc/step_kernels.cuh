@@ -579,6 +579,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     for (int s = 0; s < TH / ((NT / 64) * P); ++s) {
       const int row0 = (wy * (TH / ((NT / 64) * P)) + s) * P;
       const int y0 = ty * TH + row0;
+      if (y0 >= H) break; // warp-uniform: the rest of this warp's strips lie below the grid (ragged last tile row)
       bool valid[P];
 #pragma unroll
       for (int j = 0; j < P; ++j) valid[j] = (x < W) && (y0 + j < H);

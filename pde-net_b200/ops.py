@@ -166,16 +166,23 @@ class _Rollout(torch.autograd.Function):
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
         states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
         feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
-        if keep_features is None:
+        auto = keep_features is None
+        if auto:
             keep_features = feat_bytes <= FEATURE_CACHE_BYTES
         keep_features = bool(keep_features) and any(ctx.needs_input_grad[:3])
+        feats = None
         if keep_features:
-            feats = torch.empty(steps, B, Cc * N, H, W, dtype=u0.dtype, device=u0.device)
+            try:
+                feats = torch.empty(steps, B, Cc * N, H, W, dtype=u0.dtype, device=u0.device)
+            except torch.OutOfMemoryError:
+                if not auto:
+                    raise
+                keep_features = False  # no room: the reverse pass recomputes the features instead
+        if keep_features:
             _lib.check(_lib.fn("pdenet_rollout_fwd_keep", u0.dtype)(
                 _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), _ptr(feats), B, Cc, H, W, k, N, L, steps,
                 float(dt), _stream()), "pdenet_rollout_fwd_keep")
         else:
-            feats = None
             _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
                 _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
                 _stream()), "pdenet_rollout_fwd")
