@@ -420,6 +420,12 @@ def run_ours(args):
             "kernel_ms_share": {kk: (v / total_kernel_ms if total_kernel_ms else None) for kk, v in kind_ms.items()},
             "whole_pass": {"flop_per_point_step": F_TOTAL, "achieved_tflops": F_TOTAL * value / 1e12 / world,
                            "frac_of_fp64_peak": F_TOTAL * value / world / fma_peak,
+                           # the peak probe runs for milliseconds at the full boost clock; a long run can
+                           # sit at the board's power limit (clocks.reasons): same fraction against the
+                           # peak scaled to the median SM clock sampled during the timed region
+                           "frac_of_fp64_peak_at_sampled_clock": (
+                               F_TOTAL * value / world / (fma_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])
+                               if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None),
                            "hbm_gbs": BYTES_PER_POINT_STEP * value / 1e9 / world,
                            "frac_of_hbm_peak": BYTES_PER_POINT_STEP * value / 1e9 / world / hbm_peak,
                            "hbm_peak_source": hbm_src},

@@ -214,6 +214,27 @@ PDENET_API int pdenet_slab_step_bwd_p2p_f32(const float *u_ext, const float *lam
                                  int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
                                  size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
                                  void *stream);
+/* Feature-keeping slab steps (see pdenet_rollout_fwd_keep): the forward step also stores the C*N
+ * derivative features of its OWNED rows, feats [B,C*N,Hs,W]; the reverse step reads them for the
+ * owned rows and recomputes only the ghost rows.  Peers may be NULL with mirror_rows = 0. */
+PDENET_API int pdenet_slab_step_fwd_keep_f64(const double *u_ext, const double *kernels, const double *symnet, double *out,
+                                  double *feats, double *peer_up_out, double *peer_down_out, int mirror_rows, int B,
+                                  int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
+                                  int N, int L, double dt, void *stream);
+PDENET_API int pdenet_slab_step_fwd_keep_f32(const float *u_ext, const float *kernels, const float *symnet, float *out,
+                                  float *feats, float *peer_up_out, float *peer_down_out, int mirror_rows, int B, int C,
+                                  int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N,
+                                  int L, double dt, void *stream);
+PDENET_API int pdenet_slab_step_bwd_kept_f64(const double *u_ext, const double *lam_ext, const double *feats,
+                                  const double *kernels, const double *symnet, double *lam_out, double *peer_up_out,
+                                  double *peer_down_out, int mirror_rows, int out_rows_per_image, int out_row_offset,
+                                  void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
+                                  int L, double dt, void *stream);
+PDENET_API int pdenet_slab_step_bwd_kept_f32(const float *u_ext, const float *lam_ext, const float *feats, const float *kernels,
+                                  const float *symnet, float *lam_out, float *peer_up_out, float *peer_down_out,
+                                  int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                  size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                  void *stream);
 PDENET_API int pdenet_slab_bwd_end_f64(void *workspace, size_t workspace_bytes, double *grad_kernels, double *grad_symnet,
                             int B, int C, int Hs, int W, int k, int N, int L, void *stream);
 PDENET_API int pdenet_slab_bwd_end_f32(void *workspace, size_t workspace_bytes, float *grad_kernels, float *grad_symnet,

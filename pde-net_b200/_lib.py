@@ -40,6 +40,8 @@ _PROTOS = {
     "pdenet_slab_step_fwd_{t}": (_i, [_vp] * 4 + [_i] * 10 + [_d, _vp]),
     "pdenet_slab_step_fwd_p2p_{t}": (_i, [_vp] * 6 + [_i] * 11 + [_d, _vp]),
     "pdenet_slab_step_bwd_p2p_{t}": (_i, [_vp] * 7 + [_i, _i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
+    "pdenet_slab_step_fwd_keep_{t}": (_i, [_vp] * 7 + [_i] * 11 + [_d, _vp]),
+    "pdenet_slab_step_bwd_kept_{t}": (_i, [_vp] * 8 + [_i, _i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
     "pdenet_slab_bwd_workspace_bytes": (_sz, [_i] * 8),
     "pdenet_slab_bwd_begin": (_i, [_vp, _sz] + [_i] * 8 + [_vp]),
     "pdenet_slab_step_bwd_{t}": (_i, [_vp] * 5 + [_i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),

@@ -434,7 +434,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
 }
 
 template <typename T>
-static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *out, T *peer_up, T *peer_dn,
+static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *out, T *feats, T *peer_up, T *peer_dn,
                          int mirror_rows, int B, int C, int Hs, int W, int halo, int out_rows, int out_off, int k,
                          int N, int L, double dt, void *stream) {
   if (mirror_rows < 0 || mirror_rows > Hs || mirror_rows > out_off || (mirror_rows > 0 && (!peer_up || !peer_dn)) ||
@@ -463,6 +463,7 @@ static int slab_step_fwd(const T *u_ext, const T *kernels, const T *symnet, T *o
   p.peer_up = peer_up;
   p.peer_dn = peer_dn;
   p.mirror_rows = mirror_rows;
+  p.feats = feats; // [B][C*N][Hs][W]: features of the owned rows, kept for the reverse step (may be NULL)
   int rc = 0;
   PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, Hs, W, (cudaStream_t)stream)));
   return rc;
@@ -491,8 +492,8 @@ static SlabLayout slab_layout(size_t es, int B, int C, int Hs, int W, int k, int
 }
 
 template <typename T>
-static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, const T *symnet, T *lam_out, T *peer_up,
-                         T *peer_dn, int mirror_rows, int out_rows, int out_off, void *workspace, size_t ws_bytes,
+static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *feats, const T *kernels, const T *symnet,
+                         T *lam_out, T *peer_up, T *peer_dn, int mirror_rows, int out_rows, int out_off, void *workspace, size_t ws_bytes,
                          int B, int C, int Hs, int W, int k, int N, int L, double dt, void *stream) {
   if (mirror_rows < 0 || mirror_rows > Hs || mirror_rows > out_off || (mirror_rows > 0 && (!peer_up || !peer_dn)) ||
       out_rows < Hs + out_off + mirror_rows)
@@ -536,8 +537,11 @@ static int slab_step_bwd(const T *u_ext, const T *lam_ext, const T *kernels, con
     p.g_off = r + row0[part];
     p.sym_partial = (double *)(ws + lay.off_sym);
     p.skip_sym_grad = part != 0;
+    // owned rows: read the features the forward step kept, if any; ghost rows are always recomputed
+    const bool kept = part == 0 && feats;
+    p.feats = kept ? const_cast<T *>(feats) : nullptr;
     int rc = 0;
-    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_BWD_A, N, C, VL, p, B, nrows[part], W, st)));
+    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(kept ? MODE_BWD_A_KEPT : MODE_BWD_A, N, C, VL, p, B, nrows[part], W, st)));
     if (rc) return rc;
   }
   AdjParams<T> q;
@@ -1188,13 +1192,13 @@ int pdenet_linear_rollout_bwd_f32(const float *u0, const float *states, const fl
 int pdenet_slab_step_fwd_f64(const double *u_ext, const double *kernels, const double *symnet, double *out, int B,
                              int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
                              int N, int L, double dt, void *st) {
-  return slab_step_fwd<double>(u_ext, kernels, symnet, out, nullptr, nullptr, 0, B, C, Hs, W, halo,
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, nullptr, nullptr, nullptr, 0, B, C, Hs, W, halo,
                                out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 int pdenet_slab_step_fwd_f32(const float *u_ext, const float *kernels, const float *symnet, float *out, int B, int C,
                              int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N,
                              int L, double dt, void *st) {
-  return slab_step_fwd<float>(u_ext, kernels, symnet, out, nullptr, nullptr, 0, B, C, Hs, W, halo,
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, nullptr, nullptr, nullptr, 0, B, C, Hs, W, halo,
                               out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 
@@ -1221,28 +1225,28 @@ int pdenet_slab_step_bwd_f64(const double *u_ext, const double *lam_ext, const d
                              const double *symnet, double *lam_out, int out_rows_per_image, int out_row_offset,
                              void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
                              int L, double dt, void *st) {
-  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
+  return slab_step_bwd<double>(u_ext, lam_ext, nullptr, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
                                out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
 }
 int pdenet_slab_step_bwd_f32(const float *u_ext, const float *lam_ext, const float *kernels, const float *symnet,
                              float *lam_out, int out_rows_per_image, int out_row_offset, void *workspace,
                              size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
                              void *st) {
-  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
+  return slab_step_bwd<float>(u_ext, lam_ext, nullptr, kernels, symnet, lam_out, nullptr, nullptr, 0, out_rows_per_image,
                               out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt, st);
 }
 int pdenet_slab_step_fwd_p2p_f64(const double *u_ext, const double *kernels, const double *symnet, double *out,
                                  double *peer_up_out, double *peer_down_out, int mirror_rows, int B, int C, int Hs,
                                  int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
                                  double dt, void *st) {
-  return slab_step_fwd<double>(u_ext, kernels, symnet, out, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, nullptr, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
                                out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 int pdenet_slab_step_fwd_p2p_f32(const float *u_ext, const float *kernels, const float *symnet, float *out,
                                  float *peer_up_out, float *peer_down_out, int mirror_rows, int B, int C, int Hs,
                                  int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N, int L,
                                  double dt, void *st) {
-  return slab_step_fwd<float>(u_ext, kernels, symnet, out, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, nullptr, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W, halo,
                               out_rows_per_image, out_row_offset, k, N, L, dt, st);
 }
 int pdenet_slab_step_bwd_p2p_f64(const double *u_ext, const double *lam_ext, const double *kernels,
@@ -1250,7 +1254,7 @@ int pdenet_slab_step_bwd_p2p_f64(const double *u_ext, const double *lam_ext, con
                                  int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
                                  size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
                                  void *st) {
-  return slab_step_bwd<double>(u_ext, lam_ext, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+  return slab_step_bwd<double>(u_ext, lam_ext, nullptr, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
                                out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L,
                                dt, st);
 }
@@ -1259,7 +1263,43 @@ int pdenet_slab_step_bwd_p2p_f32(const float *u_ext, const float *lam_ext, const
                                  int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
                                  size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
                                  void *st) {
-  return slab_step_bwd<float>(u_ext, lam_ext, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+  return slab_step_bwd<float>(u_ext, lam_ext, nullptr, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+                              out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt,
+                              st);
+}
+int pdenet_slab_step_fwd_keep_f64(const double *u_ext, const double *kernels, const double *symnet, double *out,
+                                  double *feats, double *peer_up_out, double *peer_down_out, int mirror_rows, int B,
+                                  int C, int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k,
+                                  int N, int L, double dt, void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return slab_step_fwd<double>(u_ext, kernels, symnet, out, feats, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W,
+                               halo, out_rows_per_image, out_row_offset, k, N, L, dt, st);
+}
+int pdenet_slab_step_fwd_keep_f32(const float *u_ext, const float *kernels, const float *symnet, float *out,
+                                  float *feats, float *peer_up_out, float *peer_down_out, int mirror_rows, int B, int C,
+                                  int Hs, int W, int halo, int out_rows_per_image, int out_row_offset, int k, int N,
+                                  int L, double dt, void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return slab_step_fwd<float>(u_ext, kernels, symnet, out, feats, peer_up_out, peer_down_out, mirror_rows, B, C, Hs, W,
+                              halo, out_rows_per_image, out_row_offset, k, N, L, dt, st);
+}
+int pdenet_slab_step_bwd_kept_f64(const double *u_ext, const double *lam_ext, const double *feats,
+                                  const double *kernels, const double *symnet, double *lam_out, double *peer_up_out,
+                                  double *peer_down_out, int mirror_rows, int out_rows_per_image, int out_row_offset,
+                                  void *workspace, size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N,
+                                  int L, double dt, void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return slab_step_bwd<double>(u_ext, lam_ext, feats, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
+                               out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L,
+                               dt, st);
+}
+int pdenet_slab_step_bwd_kept_f32(const float *u_ext, const float *lam_ext, const float *feats, const float *kernels,
+                                  const float *symnet, float *lam_out, float *peer_up_out, float *peer_down_out,
+                                  int mirror_rows, int out_rows_per_image, int out_row_offset, void *workspace,
+                                  size_t workspace_bytes, int B, int C, int Hs, int W, int k, int N, int L, double dt,
+                                  void *st) {
+  if (!feats) return PDENET_E_BADARG;
+  return slab_step_bwd<float>(u_ext, lam_ext, feats, kernels, symnet, lam_out, peer_up_out, peer_down_out, mirror_rows,
                               out_rows_per_image, out_row_offset, workspace, workspace_bytes, B, C, Hs, W, k, N, L, dt,
                               st);
 }

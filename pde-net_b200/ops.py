@@ -298,13 +298,14 @@ def linear_rollout(u0, id_kernel, kernels, coe, dt: float, steps: int, last_only
 
 def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, halo: int,
               out: Optional[torch.Tensor] = None, out_row_offset: int = 0, peer_up: int = 0, peer_dn: int = 0,
-              mirror_rows: int = 0) -> torch.Tensor:
+              mirror_rows: int = 0, feats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One forward step on a slab [B,C,Hs+2*halo,W] whose ghost rows are already filled
     (slab domain decomposition).  Writes rows [out_row_offset, out_row_offset+Hs)
     of ``out`` (default: a fresh [B,C,Hs,W]).  With ``mirror_rows > 0`` the kernel also stores its
     first / last ``mirror_rows`` rows into the ring neighbours' output buffers (``peer_up`` /
     ``peer_dn``: raw device pointers of the neighbours' buffers mapped into this process) -- the
-    halo exchange fused into the step over NVLink peer memory."""
+    halo exchange fused into the step over NVLink peer memory.  ``feats`` [B,C*N,Hs,W] (optional)
+    receives the derivative features of the owned rows for :class:`SlabBackward`."""
     u_ext = _req(u_ext.detach(), "u_ext")
     kernels = _req(kernels.detach(), "kernels", u_ext.dtype)
     symnet = _req(symnet.detach(), "symnet", u_ext.dtype)
@@ -315,6 +316,15 @@ def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, 
         out = torch.empty(B, Cc, Hs, W, dtype=u_ext.dtype, device=u_ext.device)
     if not out.is_contiguous():
         raise ValueError("out must be contiguous")
+    if feats is not None:
+        feats = _req(feats, "feats", u_ext.dtype)
+        if tuple(feats.shape) != (B, Cc * N, Hs, W):
+            raise ValueError("feats must be [B, C*N, Hs, W]")
+        _lib.check(_lib.fn("pdenet_slab_step_fwd_keep", u_ext.dtype)(
+            _ptr(u_ext), _ptr(kernels), _ptr(symnet), _ptr(out), _ptr(feats), C.c_void_p(peer_up or None),
+            C.c_void_p(peer_dn or None), mirror_rows, B, Cc, Hs, W, halo, out.shape[2], out_row_offset, k, N, L,
+            float(dt), _stream()), "pdenet_slab_step_fwd_keep")
+        return out
     _lib.check(_lib.fn("pdenet_slab_step_fwd_p2p", u_ext.dtype)(
         _ptr(u_ext), _ptr(kernels), _ptr(symnet), _ptr(out), C.c_void_p(peer_up or None), C.c_void_p(peer_dn or None),
         mirror_rows, B, Cc, Hs, W, halo, out.shape[2], out_row_offset, k, N, L, float(dt), _stream()),
@@ -376,7 +386,7 @@ class SlabBackward:
                                                     _stream()), "pdenet_slab_bwd_begin")
 
     def step(self, u_ext2: torch.Tensor, lam_ext: torch.Tensor, lam_out: torch.Tensor, out_row_offset: int = 0,
-             peer_up: int = 0, peer_dn: int = 0, mirror_rows: int = 0):
+             peer_up: int = 0, peer_dn: int = 0, mirror_rows: int = 0, feats: Optional[torch.Tensor] = None):
         dt_ = self.kernels.dtype
         u_ext2, lam_ext = _req(u_ext2, "u_ext2", dt_), _req(lam_ext, "lam_ext", dt_)
         if tuple(u_ext2.shape) != (self.B, self.C, self.Hs + 4 * self.r, self.W):
@@ -385,6 +395,16 @@ class SlabBackward:
             raise ValueError("lam_ext must carry r ghost rows on each side")
         if not lam_out.is_contiguous():
             raise ValueError("lam_out must be contiguous")
+        if feats is not None:  # the forward step kept the features of the owned rows
+            feats = _req(feats, "feats", dt_)
+            if tuple(feats.shape) != (self.B, self.C * self.N, self.Hs, self.W):
+                raise ValueError("feats must be [B, C*N, Hs, W]")
+            _lib.check(_lib.fn("pdenet_slab_step_bwd_kept", dt_)(
+                _ptr(u_ext2), _ptr(lam_ext), _ptr(feats), _ptr(self.kernels), _ptr(self.symnet), _ptr(lam_out),
+                C.c_void_p(peer_up or None), C.c_void_p(peer_dn or None), mirror_rows, lam_out.shape[2],
+                out_row_offset, _ptr(self.ws), self.nbytes, self.B, self.C, self.Hs, self.W, self.k, self.N, self.L,
+                self.dt, _stream()), "pdenet_slab_step_bwd_kept")
+            return lam_out
         _lib.check(_lib.fn("pdenet_slab_step_bwd_p2p", dt_)(
             _ptr(u_ext2), _ptr(lam_ext), _ptr(self.kernels), _ptr(self.symnet), _ptr(lam_out),
             C.c_void_p(peer_up or None), C.c_void_p(peer_dn or None), mirror_rows, lam_out.shape[2], out_row_offset,

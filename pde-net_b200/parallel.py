@@ -122,7 +122,7 @@ class SlabDecomposition:
 
     def rollout_fwd_bwd(self, u_local: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float,
                         steps: int, grad_last_local: Callable, step_fn: Optional[Callable] = None,
-                        bwd_factory: Optional[Callable] = None):
+                        bwd_factory: Optional[Callable] = None, keep_features: Optional[bool] = None):
         """Forward rollout on this rank's slab, then the reverse pass.
 
         ``grad_last_local(final_local) -> dLoss/d(final state)`` for the owned rows (the loss is
@@ -134,8 +134,13 @@ class SlabDecomposition:
         No full-slab copies: every forward state lives in its own buffer with 2r ghost rows (the
         forward exchanges 2r rows, so the reverse pass needs no state exchange at all), each step
         writes straight into the interior of the next buffer, and the reverse step writes the new
-        adjoint into the interior of the next r-ghosted adjoint buffer."""
+        adjoint into the interior of the next r-ghosted adjoint buffer.
+
+        ``keep_features`` (CUDA steps only): the forward steps keep the derivative features of the
+        owned rows and the reverse steps read them instead of recomputing the stencils (ghost rows
+        are always recomputed); None = keep when they fit ``ops.FEATURE_CACHE_BYTES``."""
         from . import ops
+        cuda_steps = step_fn is None and bwd_factory is None
         if step_fn is None:
             step_fn = ops.slab_step
         if bwd_factory is None:
@@ -143,11 +148,16 @@ class SlabDecomposition:
         h = self.halo
         h2 = 2 * h
         B, C, Hs, W = u_local.shape
+        feats = _slab_feature_buffers(keep_features if cuda_steps else False, steps, B, C, kernels.shape[0], Hs, W,
+                                      u_local)
         bufs = [self.extend(u_local, h2)]            # u_0 .. u_steps, each with 2r ghost rows
-        for _ in range(steps):
+        for t in range(steps):
             self.exchange(bufs[-1], h2)
             nxt = torch.empty_like(bufs[-1])
-            step_fn(bufs[-1], kernels, symnet, L, dt, h2, nxt, h2)
+            if feats is not None:
+                step_fn(bufs[-1], kernels, symnet, L, dt, h2, nxt, h2, feats=feats[t])
+            else:
+                step_fn(bufs[-1], kernels, symnet, L, dt, h2, nxt, h2)
             bufs.append(nxt)
         final = bufs[-1][:, :, h2:h2 + Hs].contiguous()
         lam_ext = self.extend(grad_last_local(final).contiguous(), h)
@@ -155,11 +165,25 @@ class SlabDecomposition:
         bwd = bwd_factory(kernels, symnet, L, dt, B, C, Hs, W)
         for t in range(steps - 1, -1, -1):
             self.exchange(lam_ext, h)
-            bwd.step(bufs[t], lam_ext, lam_nxt, h)   # bufs[t] already carries its 2r ghost rows
+            if feats is not None:
+                bwd.step(bufs[t], lam_ext, lam_nxt, h, feats=feats[t])
+            else:
+                bwd.step(bufs[t], lam_ext, lam_nxt, h)   # bufs[t] already carries its 2r ghost rows
             lam_ext, lam_nxt = lam_nxt, lam_ext
         gk, gs = bwd.finish()
         flat_allreduce([gk, gs], group=self.group)
         return final, lam_ext[:, :, h:h + Hs].contiguous(), gk, gs
+
+
+def _slab_feature_buffers(keep, steps, B, C, N, Hs, W, like: torch.Tensor):
+    """[steps, B, C*N, Hs, W] buffer for the kept features of a slab rollout, or None."""
+    from . import ops
+    nbytes = steps * B * C * N * Hs * W * like.element_size()
+    if keep is None:
+        keep = nbytes <= ops.FEATURE_CACHE_BYTES
+    if not keep:
+        return None
+    return torch.empty(steps, B, C * N, Hs, W, dtype=like.dtype, device=like.device)
 
 
 class SlabPeerBuffers:
@@ -206,19 +230,21 @@ class SlabPeerBuffers:
 
 def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u_local: torch.Tensor,
                              kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
-                             grad_last_local: Callable):
+                             grad_last_local: Callable, keep_features: Optional[bool] = None):
     """``SlabDecomposition.rollout_fwd_bwd`` with the halo exchanges fused into the step kernels
     (peer stores into the neighbours' ghost rows, `SlabPeerBuffers`).  Only the initial state and
     the loss seed need a conventional ghost fill."""
     from . import ops
     h, h2, Hs = slab.halo, 2 * slab.halo, slab.Hs
     B, C, _, W = u_local.shape
+    feats = _slab_feature_buffers(keep_features, steps, B, C, kernels.shape[0], Hs, W, u_local)
     bufs.state[0][:, :, h2:h2 + Hs] = u_local
     slab.exchange(bufs.state[0], h2)
     bufs.barrier()                                   # every rank's buffers are ready to be written
     for t in range(steps):
         up, dn = bufs.state_peers(t + 1)
-        ops.slab_step(bufs.state[t], kernels, symnet, L, dt, h2, bufs.state[t + 1], h2, up, dn, h2)
+        ops.slab_step(bufs.state[t], kernels, symnet, L, dt, h2, bufs.state[t + 1], h2, up, dn, h2,
+                      feats=None if feats is None else feats[t])
         bufs.barrier()                               # neighbours' boundary rows have landed
     final = bufs.state[steps][:, :, h2:h2 + Hs].contiguous()
     cur = 0
@@ -227,7 +253,8 @@ def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u
     bwd = ops.SlabBackward(kernels, symnet, L, dt, B, C, Hs, W)
     for t in range(steps - 1, -1, -1):
         up, dn = bufs.lam_peers(cur ^ 1)
-        bwd.step(bufs.state[t], bufs.lam[cur], bufs.lam[cur ^ 1], h, up, dn, h)
+        bwd.step(bufs.state[t], bufs.lam[cur], bufs.lam[cur ^ 1], h, up, dn, h,
+                 feats=None if feats is None else feats[t])
         bufs.barrier()
         cur ^= 1
     gk, gs = bwd.finish()

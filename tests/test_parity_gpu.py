@@ -426,7 +426,8 @@ def test_slab_rollout_single_rank(P, cuda_device):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64])
-def test_slab_fwd_bwd_single_rank_matches_autograd(P, cuda_device, dtype):
+@pytest.mark.parametrize("keep", [False, True])
+def test_slab_fwd_bwd_single_rank_matches_autograd(P, cuda_device, dtype, keep):
     """Slab reverse pass (ghost-row recompute, no wrap in H) == the periodic rollout's autograd."""
     from pdenet_b200 import parallel as PP
     k, max_order, C, L, dx, dt, steps = 7, 2, 2, 2, 0.1, 1e-3, 3
@@ -438,14 +439,16 @@ def test_slab_fwd_bwd_single_rank_matches_autograd(P, cuda_device, dtype):
     ud, Kd, sd = [t.clone().requires_grad_(True) for t in (u, Ks, sym)]
     ref = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True)
     (ref * w).sum().backward()
-    fin, gu, gk, gs = PP.SlabDecomposition(48, 3, 0, 1).rollout_fwd_bwd(u, Ks, sym, L, dt, steps, lambda f: w)
+    fin, gu, gk, gs = PP.SlabDecomposition(48, 3, 0, 1).rollout_fwd_bwd(u, Ks, sym, L, dt, steps, lambda f: w,
+                                                                        keep_features=keep)
     assert torch.equal(fin, ref.detach())
     assert rel(gu, ud.grad) < 1e-12
     assert rel(gk, Kd.grad) < 1e-12
     assert rel(gs, sd.grad) < 1e-12
 
 
-def test_slab_p2p_single_rank_matches_autograd(P, cuda_device):
+@pytest.mark.parametrize("keep", [False, True])
+def test_slab_p2p_single_rank_matches_autograd(P, cuda_device, keep):
     """Fused halo writes (peer stores) with the rank as its own neighbour (world 1)."""
     from pdenet_b200 import parallel as PP
     k, max_order, C, L, dx, dt, steps = 7, 2, 2, 2, 0.1, 1e-3, 3
@@ -459,7 +462,8 @@ def test_slab_p2p_single_rank_matches_autograd(P, cuda_device):
     (ref * w).sum().backward()
     slab = PP.SlabDecomposition(48, 3, 0, 1)
     bufs = PP.SlabPeerBuffers(slab, 2, C, 40, steps, torch.float64, cuda_device)
-    fin, gu, gk, gs = PP.slab_rollout_fwd_bwd_p2p(slab, bufs, u, Ks, sym, L, dt, steps, lambda f: w)
+    fin, gu, gk, gs = PP.slab_rollout_fwd_bwd_p2p(slab, bufs, u, Ks, sym, L, dt, steps, lambda f: w,
+                                                  keep_features=keep)
     assert torch.equal(fin, ref.detach())
     assert rel(gu, ud.grad) < 1e-12
     assert rel(gk, Kd.grad) < 1e-12

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--p2p", action="store_true", help="fused peer-memory halo writes instead of NCCL send/recv")
+    ap.add_argument("--keep", choices=["on", "off"], default="on",
+                    help="keep the derivative features of the owned rows for the reverse steps (off = recompute)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -53,10 +55,10 @@ def main():
         pb = PP.SlabPeerBuffers(slab, 1, C, W, a.steps, dtype, dev)
 
         def run():
-            return PP.slab_rollout_fwd_bwd_p2p(slab, pb, mine, Ks, sym, L, dt, a.steps, seed)
+            return PP.slab_rollout_fwd_bwd_p2p(slab, pb, mine, Ks, sym, L, dt, a.steps, seed, keep_features=a.keep == "on")
     else:
         def run():
-            return slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, a.steps, seed)
+            return slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, a.steps, seed, keep_features=a.keep == "on")
 
     fin, gu, gk, gs = run()
     torch.cuda.synchronize()
@@ -87,6 +89,7 @@ def main():
     if rank == 0:
         tol = 1e-10 * a.steps if dtype == torch.float64 else 1e-3
         out = {"what": "slab-decomposed fwd+bwd rollout, 1 trajectory" + (", fused peer halo writes" if a.p2p else ", NCCL halo exchange"), "n_gpus": world, "grid": [H, W], "dtype": a.dtype,
+               "features": "kept" if a.keep == "on" else "recomputed",
                "steps": a.steps, "ms_per_pass": ms.item(), "grid_point_steps_per_s": H * W * a.steps / (ms.item() * 1e-3),
                "max_rel_err_vs_single_gpu": None if errs is None else
                dict(zip(["state", "grad_u0", "grad_kernels", "grad_symnet"], errs.tolist()))}
