@@ -253,6 +253,25 @@ PDENET_API int pdenet_mse_seed_f32(const float *states, const float *observed, c
                         float *grad_states, double *loss_out, size_t n_per_step, int steps, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* ---- row f-2: 1-D piecewise Lagrange interpolation (source term f(u) of PDE-Net 1's
+ * SingleNonLinear2d; upstream aTEAM/nn/modules/Interpolation.py::LagrangeInterp with m = 1
+ * [recollection]) -------------------------------------------------------------------------------
+ * `mesh` cells on [lo, hi], `degree` (1..4) + 1 equispaced nodes per cell with shared end nodes;
+ * coef[mesh*degree + 1] = the values at the nodes.  y[i] = f(x[i]); points outside [lo, hi] use the
+ * first / last cell's polynomial.  Reverse: gx[i] = gy[i] f'(x[i]) (gx may be NULL),
+ * gcoef[q] = sum_i gy[i] * basis_q(x[i]) (overwritten; deterministic, no atomics). */
+PDENET_API int pdenet_lagrange1d_fwd_f64(const double *x, const double *coef, double *y, size_t n, double lo, double hi,
+                              int mesh, int degree, void *stream);
+PDENET_API int pdenet_lagrange1d_fwd_f32(const float *x, const float *coef, float *y, size_t n, double lo, double hi, int mesh,
+                              int degree, void *stream);
+PDENET_API size_t pdenet_lagrange1d_bwd_workspace_bytes(size_t n, int mesh, int degree);
+PDENET_API int pdenet_lagrange1d_bwd_f64(const double *x, const double *gy, const double *coef, double *gx, double *gcoef,
+                              size_t n, double lo, double hi, int mesh, int degree, void *workspace,
+                              size_t workspace_bytes, void *stream);
+PDENET_API int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef, float *gx, float *gcoef, size_t n,
+                              double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
+                              void *stream);
+
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
  * 2 = reverse kernel B1 (data gradient), 3 = reverse kernel B2 (filter gradient),

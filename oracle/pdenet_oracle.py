@@ -244,3 +244,30 @@ def training_loss(u0, moments, scales, pinned, symnet, L, dt, observed, block_we
     loss = loss + blocks * sparsity * huber_l1(symnet, symnet_threshold)
     loss = loss + blocks * momentsparsity * huber_l1(moments[~pinned], moment_threshold)
     return loss
+
+
+# ----------------------------------------------------------------------------- f-2
+def lagrange1d(x: torch.Tensor, coef: torch.Tensor, lo: float, hi: float, mesh: int, degree: int) -> torch.Tensor:
+    """Piecewise Lagrange interpolant of one variable (upstream ``aTEAM`` ``LagrangeInterp``, m = 1
+    [RECALL]): ``mesh`` uniform cells on [lo, hi], ``degree + 1`` equispaced nodes per cell sharing
+    the end nodes, ``coef[mesh*degree + 1]`` the node values; outside [lo, hi] the first / last
+    cell's polynomial is continued."""
+    s = (x - lo) * (mesh / (hi - lo))
+    c = torch.clamp(torch.floor(s.detach()), 0, mesh - 1).long()
+    t = s - c.to(s.dtype)
+    y = torch.zeros_like(x)
+    for j in range(degree + 1):
+        basis = torch.ones_like(x)
+        for m in range(degree + 1):
+            if m != j:
+                basis = basis * (t - m / degree) / ((j - m) / degree)
+        y = y + coef[c * degree + j] * basis
+    return y
+
+
+def single_nonlinear_step(u, K0, Ks, coe, fcoef, lo, hi, mesh, degree, dt):
+    """Row f-2 (PDE-Net 1 ``SingleNonLinear2d`` [RECALL]): ``D0*u + dt*(sum_n c_n (D_n*u) + f(u))``
+    with constant coefficients ``coe[N]`` and the interpolated source term ``f``."""
+    B, H, W = u.shape
+    fields = coe[:, None, None].expand(-1, H, W)
+    return linear_step(u, K0, Ks, fields, dt) + dt * lagrange1d(u, fcoef, lo, hi, mesh, degree)

@@ -43,6 +43,9 @@ _PROTOS = {
     "pdenet_slab_step_fwd_keep_{t}": (_i, [_vp] * 7 + [_i] * 11 + [_d, _vp]),
     "pdenet_slab_step_bwd_kept_{t}": (_i, [_vp] * 8 + [_i, _i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
     "pdenet_slab_bwd_workspace_bytes": (_sz, [_i] * 8),
+    "pdenet_lagrange1d_fwd_{t}": (_i, [_vp, _vp, _vp, _sz, _d, _d, _i, _i, _vp]),
+    "pdenet_lagrange1d_bwd_workspace_bytes": (_sz, [_sz, _i, _i]),
+    "pdenet_lagrange1d_bwd_{t}": (_i, [_vp] * 5 + [_sz, _d, _d, _i, _i, _vp, _sz, _vp]),
     "pdenet_slab_bwd_begin": (_i, [_vp, _sz] + [_i] * 8 + [_vp]),
     "pdenet_slab_step_bwd_{t}": (_i, [_vp] * 5 + [_i, _i, _vp, _sz] + [_i] * 7 + [_d, _vp]),
     "pdenet_slab_bwd_end_{t}": (_i, [_vp, _sz, _vp, _vp] + [_i] * 7 + [_vp]),

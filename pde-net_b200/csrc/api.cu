@@ -916,6 +916,65 @@ static int mse_seed(const T *states, const T *observed, const double *weights_ho
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
 
+// ---- 1-D piecewise Lagrange interpolation (row f-2: SingleNonLinear2d's source term) -----------
+static int lagrange_blocks(size_t n, int sms) {
+  size_t b = (n + kLagrangeThreads * 4 - 1) / (kLagrangeThreads * 4);
+  const size_t cap = (size_t)sms * 4;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+template <typename T>
+static int lagrange1d_fwd(const T *x, const T *coef, T *y, size_t n, double lo, double hi, int mesh, int degree,
+                          void *stream) {
+  if (!x || !coef || !y || n == 0 || mesh < 1 || !(hi > lo)) return PDENET_E_BADARG;
+  if (degree < 1 || degree > 4) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const T l = (T)lo, ih = (T)((double)mesh / (hi - lo));
+  const unsigned grid = (unsigned)((n + 1023) / 1024 < (size_t)sms * 8 ? (n + 1023) / 1024 : (size_t)sms * 8);
+  ProfScope ps(4, st);
+  switch (degree) {
+  case 1: lagrange1d_fwd_kernel<T, 1><<<grid, 256, 0, st>>>(x, coef, y, n, l, ih, mesh); break;
+  case 2: lagrange1d_fwd_kernel<T, 2><<<grid, 256, 0, st>>>(x, coef, y, n, l, ih, mesh); break;
+  case 3: lagrange1d_fwd_kernel<T, 3><<<grid, 256, 0, st>>>(x, coef, y, n, l, ih, mesh); break;
+  default: lagrange1d_fwd_kernel<T, 4><<<grid, 256, 0, st>>>(x, coef, y, n, l, ih, mesh); break;
+  }
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+template <typename T>
+static int lagrange1d_bwd(const T *x, const T *gy, const T *coef, T *gx, T *gcoef, size_t n, double lo, double hi,
+                          int mesh, int degree, void *workspace, size_t ws_bytes, void *stream) {
+  if (!x || !gy || !coef || !gcoef || !workspace || n == 0 || mesh < 1 || !(hi > lo)) return PDENET_E_BADARG;
+  if (degree < 1 || degree > 4) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const int Q = mesh * degree + 1;
+  const size_t smem = (size_t)Q * kLagrangeThreads * sizeof(double);
+  if (smem > 200 * 1024) return PDENET_E_UNSUPPORTED;
+  const int blocks = lagrange_blocks(n, sms);
+  if (ws_bytes < (size_t)blocks * Q * sizeof(double)) return PDENET_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const T l = (T)lo, ih = (T)((double)mesh / (hi - lo));
+  double *partial = (double *)workspace;
+  ProfScope ps(4, st);
+#define PDENET_LAG_CASE(D)                                                                                        \
+  {                                                                                                              \
+    auto kern = lagrange1d_bwd_kernel<T, D>;                                                                     \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)       \
+      return PDENET_E_CUDA;                                                                                      \
+    kern<<<blocks, kLagrangeThreads, smem, st>>>(x, gy, coef, gx, partial, n, l, ih, mesh);                      \
+  }
+  switch (degree) {
+  case 1: PDENET_LAG_CASE(1) break;
+  case 2: PDENET_LAG_CASE(2) break;
+  case 3: PDENET_LAG_CASE(3) break;
+  default: PDENET_LAG_CASE(4) break;
+  }
+#undef PDENET_LAG_CASE
+  reduce_flat_kernel<T><<<reduce_blocks(Q), 128, 0, st>>>(partial, blocks, Q, gcoef);
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
 // ---- FMA peak microbenchmark -----------------------------------------------------------------
 template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters, T a, T b) {
   T x[16];
@@ -1323,6 +1382,30 @@ int pdenet_mse_seed_f32(const float *states, const float *observed, const double
                         void *st) {
   return mse_seed<float>(states, observed, weights_host, grad_states, loss_out, n_per_step, steps, workspace,
                          workspace_bytes, st);
+}
+
+size_t pdenet_lagrange1d_bwd_workspace_bytes(size_t n, int mesh, int degree) {
+  const int sms = sm_count();
+  if (sms <= 0 || mesh < 1 || degree < 1) return 0;
+  return (size_t)lagrange_blocks(n, sms) * (mesh * degree + 1) * sizeof(double);
+}
+int pdenet_lagrange1d_fwd_f64(const double *x, const double *coef, double *y, size_t n, double lo, double hi, int mesh,
+                              int degree, void *st) {
+  return lagrange1d_fwd<double>(x, coef, y, n, lo, hi, mesh, degree, st);
+}
+int pdenet_lagrange1d_fwd_f32(const float *x, const float *coef, float *y, size_t n, double lo, double hi, int mesh,
+                              int degree, void *st) {
+  return lagrange1d_fwd<float>(x, coef, y, n, lo, hi, mesh, degree, st);
+}
+int pdenet_lagrange1d_bwd_f64(const double *x, const double *gy, const double *coef, double *gx, double *gcoef,
+                              size_t n, double lo, double hi, int mesh, int degree, void *workspace,
+                              size_t workspace_bytes, void *st) {
+  return lagrange1d_bwd<double>(x, gy, coef, gx, gcoef, n, lo, hi, mesh, degree, workspace, workspace_bytes, st);
+}
+int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef, float *gx, float *gcoef, size_t n,
+                              double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
+                              void *st) {
+  return lagrange1d_bwd<float>(x, gy, coef, gx, gcoef, n, lo, hi, mesh, degree, workspace, workspace_bytes, st);
 }
 
 int pdenet_profile_enable(int on) {

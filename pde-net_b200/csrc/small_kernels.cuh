@@ -70,7 +70,84 @@ __global__ void mse_finish_kernel(const double *partial, int count, double *loss
   if (threadIdx.x == 0) *loss_out = acc;
 }
 
-// launch geometry for the two kernels above: 4 outputs (warps) per 128-thread block
+
+// ---- piecewise Lagrange interpolation on a uniform 1-D mesh (row f-2) -----------------------------
+// The nonlinear source term f(u) of PDE-Net 1's SingleNonLinear2d (aTEAM LagrangeInterp with m = 1
+// [RECALL]): `mesh` cells of width h on [lo, lo + mesh*h], DEG+1 equispaced nodes per cell (shared
+// end nodes), coefficients coef[mesh*DEG + 1] = the values at the nodes.  Points outside the mesh
+// use the first / last cell's polynomial (cell index clamped, local coordinate not).
+template <typename T, int DEG> __device__ __forceinline__ void lagrange_basis(T t, T (&l)[DEG + 1], T (&dl)[DEG + 1]) {
+#pragma unroll
+  for (int j = 0; j <= DEG; ++j) {
+    T v = T(1), dv = T(0);
+#pragma unroll
+    for (int m = 0; m <= DEG; ++m) {
+      if (m == j) continue;
+      const T inv = T(DEG) / T(j - m), fac = (t - T(m) / T(DEG)) * inv; // (t - s_m) / (s_j - s_m), s_m = m/DEG
+      dv = dv * fac + v * inv;
+      v *= fac;
+    }
+    l[j] = v;
+    dl[j] = dv;
+  }
+}
+template <typename T> __device__ __forceinline__ int lagrange_cell(T x, T lo, T inv_h, int mesh, T &t) {
+  const T s = (x - lo) * inv_h;
+  int c = (int)floor((double)s);
+  c = c < 0 ? 0 : (c >= mesh ? mesh - 1 : c);
+  t = s - (T)c;
+  return c;
+}
+template <typename T, int DEG>
+__global__ void __launch_bounds__(256) lagrange1d_fwd_kernel(const T *x, const T *coef, T *y, size_t n, T lo, T inv_h,
+                                                             int mesh) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    T t, l[DEG + 1], dl[DEG + 1];
+    const int c = lagrange_cell(x[i], lo, inv_h, mesh, t);
+    lagrange_basis<T, DEG>(t, l, dl);
+    T v = T(0);
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) v = fma_(coef[c * DEG + j], l[j], v);
+    y[i] = v;
+  }
+}
+// gx[i] = gy[i] * f'(x[i]) (may be NULL); partial[block][q] = this block's share of dLoss/dcoef[q].
+// Every thread owns private bins in shared memory ([Q][NT] doubles), the block sums them in a fixed
+// order: deterministic, no atomics.
+constexpr int kLagrangeThreads = 128;
+template <typename T, int DEG>
+__global__ void __launch_bounds__(kLagrangeThreads) lagrange1d_bwd_kernel(const T *x, const T *gy, const T *coef, T *gx,
+                                                                          double *partial, size_t n, T lo, T inv_h,
+                                                                          int mesh) {
+  extern __shared__ double bins[]; // [Q][NT]
+  constexpr int NT = kLagrangeThreads;
+  const int Q = mesh * DEG + 1, tid = threadIdx.x;
+  for (int q = 0; q < Q; ++q) bins[q * NT + tid] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * NT + tid; i < n; i += (size_t)gridDim.x * NT) {
+    T t, l[DEG + 1], dl[DEG + 1];
+    const int c = lagrange_cell(x[i], lo, inv_h, mesh, t);
+    lagrange_basis<T, DEG>(t, l, dl);
+    const T g = gy[i];
+    T d = T(0);
+#pragma unroll
+    for (int j = 0; j <= DEG; ++j) {
+      d = fma_(coef[c * DEG + j], dl[j], d);
+      bins[(c * DEG + j) * NT + tid] += (double)g * (double)l[j];
+    }
+    if (gx) gx[i] = g * d * inv_h;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int q = warp; q < Q; q += NT / 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) s += bins[q * NT + k * 32 + lane];
+    s = warp_sum_fixed(s);
+    if (lane == 0) partial[(size_t)blockIdx.x * Q + q] = s;
+  }
+}
+
+// launch geometry for the two reduce kernels: 4 outputs (warps) per 128-thread block
 inline unsigned reduce_blocks(int n_out) { return (unsigned)((n_out + 3) / 4); }
 
 } // namespace pdenet

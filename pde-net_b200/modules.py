@@ -326,3 +326,74 @@ class VariantCoeLinear2d(nn.Module):
         ks = self.scaled_kernels()
         return ops.linear_rollout(init, ks[0], ks[1:], self.coefficient_fields(), self.dt, int(stepnum),
                                   last_only=not all_states)
+
+
+class LagrangeInterp1d(nn.Module):
+    """Learnable piecewise Lagrange polynomial of one variable on a uniform mesh (upstream
+    ``aTEAM.nn.modules.Interpolation.LagrangeInterp`` with m = 1 [RECALL]): ``interp_coe``
+    [mesh_size*degree + 1] are the node values, zero-initialised; ``forward(x)`` evaluates it at
+    every entry of ``x`` with the CUDA op ``ops.lagrange1d``."""
+
+    def __init__(self, degree: int, mesh_bound, mesh_size: int, dtype=torch.float64):
+        super().__init__()
+        self.degree, self.mesh_size = int(degree), int(mesh_size)
+        self.mesh_bound = (float(mesh_bound[0]), float(mesh_bound[1]))
+        self.interp_coe = nn.Parameter(torch.zeros(self.mesh_size * self.degree + 1, dtype=dtype))
+
+    def nodes(self) -> torch.Tensor:
+        """Positions of the interpolation nodes (for initialising ``interp_coe`` from a function)."""
+        lo, hi = self.mesh_bound
+        return torch.linspace(lo, hi, self.mesh_size * self.degree + 1, dtype=self.interp_coe.dtype,
+                              device=self.interp_coe.device)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.lagrange1d(x, self.interp_coe, self.mesh_bound[0], self.mesh_bound[1], self.mesh_size, self.degree)
+
+
+class SingleNonLinear2d(nn.Module):
+    """PDE-Net 1 model with a nonlinear source term (upstream branch ``PDE-Net``,
+    ``SingleNonLinear2d`` [RECALL]):
+    ``u+ = D0*u + dt * (sum_n c_n (D_n*u) + f(u))`` with learnable filters, one learnable constant
+    coefficient c_n per derivative term and ``f`` a learnable piecewise Lagrange polynomial.
+
+    Each step is one fused linear step (``ops.linear_rollout`` with the constants broadcast to
+    fields) plus the interpolation op; unlike the two headline models the steps of a rollout are
+    not fused into one call yet (the source term sits between them)."""
+
+    def __init__(self, kernel_size, max_order, dx, dt, constraint="moment", nonlinear_interp_degree=2,
+                 nonlinear_interp_mesh_bound=(-15.0, 15.0), nonlinear_interp_mesh_size=20, dtype=torch.float64):
+        super().__init__()
+        self.dt, self.dx = float(dt), _pair(dx)
+        self.kernel_size, self.max_order = kernel_size, max_order
+        self.orders = [o for o in order_list(max_order) if o != (0, 0)]
+        self.id = FD2d(kernel_size, (0, 0), dx=dx, constraint=constraint)
+        self._fd_names = []
+        for (o0, o1) in self.orders:
+            name = "fd%d%d" % (o0, o1)
+            self.add_module(name, FD2d(kernel_size, (o0, o1), dx=dx, constraint=constraint))
+            self._fd_names.append(name)
+        self.coe = nn.Parameter(torch.zeros(len(self.orders), dtype=torch.float64))
+        self.nonlinearfitter = LagrangeInterp1d(nonlinear_interp_degree, nonlinear_interp_mesh_bound,
+                                                nonlinear_interp_mesh_size)
+        self.to(dtype)
+
+    fds = VariantCoeLinear2d.fds
+    diff_x_proj = VariantCoeLinear2d.diff_x_proj
+    diff_grad_proj = VariantCoeLinear2d.diff_grad_proj
+    scaled_kernels = VariantCoeLinear2d.scaled_kernels
+
+    def diff_params(self):
+        return (fd.moment for fd in [self.id] + self.fds)
+
+    def coe_params(self):
+        return iter([self.coe, self.nonlinearfitter.interp_coe])
+
+    def forward(self, init: torch.Tensor, stepnum: int) -> torch.Tensor:
+        ks = self.scaled_kernels()
+        B, H, W = init.shape
+        fields = self.coe[:, None, None].expand(-1, H, W).contiguous()
+        u = init
+        for _ in range(int(stepnum)):
+            u = ops.linear_rollout(u, ks[0], ks[1:], fields, self.dt, 1, last_only=True) \
+                + self.dt * self.nonlinearfitter(u)
+        return u

@@ -332,6 +332,47 @@ def slab_step(u_ext: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, 
     return out
 
 
+# ------------------------------------------------------------------------------ row f-2
+class _Lagrange1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coef, lo, hi, mesh, degree):
+        x = _req(x, "x")
+        coef = _req(coef, "coef", x.dtype)
+        if coef.numel() != mesh * degree + 1:
+            raise ValueError("coef must hold mesh*degree + 1 = %d node values" % (mesh * degree + 1))
+        y = torch.empty_like(x)
+        if x.numel():
+            _lib.check(_lib.fn("pdenet_lagrange1d_fwd", x.dtype)(_ptr(x), _ptr(coef), _ptr(y), x.numel(), lo, hi, mesh,
+                                                                 degree, _stream()), "pdenet_lagrange1d_fwd")
+        ctx.save_for_backward(x, coef)
+        ctx.cfg = (lo, hi, mesh, degree)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, coef = ctx.saved_tensors
+        lo, hi, mesh, degree = ctx.cfg
+        gy = _req(gy, "grad", x.dtype)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gc = torch.zeros_like(coef)
+        if x.numel():
+            nbytes = _lib.lib().pdenet_lagrange1d_bwd_workspace_bytes(x.numel(), mesh, degree)
+            ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=x.device)
+            _lib.check(_lib.fn("pdenet_lagrange1d_bwd", x.dtype)(
+                _ptr(x), _ptr(gy), _ptr(coef), _ptr(gx), _ptr(gc), x.numel(), lo, hi, mesh, degree, _ptr(ws), nbytes,
+                _stream()), "pdenet_lagrange1d_bwd")
+        elif gx is not None:
+            gx.zero_()
+        return gx, gc, None, None, None, None
+
+
+def lagrange1d(x: torch.Tensor, coef: torch.Tensor, lo: float, hi: float, mesh: int, degree: int) -> torch.Tensor:
+    """Piecewise Lagrange interpolant of degree ``degree`` on ``mesh`` uniform cells of [lo, hi],
+    evaluated at every entry of ``x`` (any shape); ``coef`` [mesh*degree + 1] are the node values.
+    The nonlinear source term of PDE-Net 1's ``SingleNonLinear2d``."""
+    return _Lagrange1d.apply(x, coef, float(lo), float(hi), int(mesh), int(degree))
+
+
 class _MseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, states, observed, weights):

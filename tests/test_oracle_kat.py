@@ -201,3 +201,25 @@ def test_linear_step_matches_manual():
     d = ONP.fd2d_apply(u[:, None].numpy(), torch.cat([K0[None], Ks]).numpy())
     ref = d[:, 0] + 1.5e-2 * (coe.numpy()[None] * d[:, 1:]).sum(1)
     assert np.abs(out.numpy() - ref).max() < 1e-11
+
+
+# ----------------------------------------------------------------------------- f-2 (KAT-8)
+@pytest.mark.parametrize("degree", [1, 2, 3, 4])
+def test_kat8_lagrange1d_reproduces_polynomials_and_nodes(degree):
+    """The piecewise interpolant of degree d is exact for any polynomial of degree <= d (also when
+    continued outside the mesh), hits its node values, and is continuous across cells."""
+    mesh, lo, hi = 5, -1.0, 2.0
+    nodes = torch.linspace(lo, hi, mesh * degree + 1, dtype=torch.float64)
+
+    def f(x):
+        return 0.3 * x ** degree - x + 0.5
+
+    x = torch.linspace(-1.5, 2.5, 401, dtype=torch.float64)
+    assert (O.lagrange1d(x, f(nodes), lo, hi, mesh, degree) - f(x)).abs().max() < 1e-12
+    g = torch.Generator().manual_seed(degree)
+    coef = torch.randn(mesh * degree + 1, generator=g, dtype=torch.float64)
+    assert (O.lagrange1d(nodes, coef, lo, hi, mesh, degree) - coef).abs().max() < 1e-13
+    edges = torch.linspace(lo, hi, mesh + 1, dtype=torch.float64)[1:-1]
+    left = O.lagrange1d(edges - 1e-9, coef, lo, hi, mesh, degree)
+    right = O.lagrange1d(edges + 1e-9, coef, lo, hi, mesh, degree)
+    assert (left - right).abs().max() < 1e-6

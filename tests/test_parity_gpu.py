@@ -592,6 +592,67 @@ def test_mse_loss_seed(P, cuda_device, dtype):
     assert loss2.item() == loss.item()  # deterministic
 
 
+# ------------------------------------------------------------------ row f-2
+@pytest.mark.parametrize("degree", [1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_lagrange1d_matches_oracle(P, cuda_device, degree, dtype):
+    """Interpolated source term: values, input gradient and node gradients (deterministic)."""
+    g = torch.Generator().manual_seed(100 + degree)
+    mesh, lo, hi = 7, -2.0, 3.0
+    coef = torch.randn(mesh * degree + 1, generator=g, dtype=torch.float64)
+    x = (torch.rand(3, 37, 29, generator=g, dtype=torch.float64) * 6.4 - 2.7)   # some points outside [lo, hi]
+    x[0, 0, :4] = torch.tensor([lo, hi, lo + (hi - lo) / mesh, 0.0])            # on cell boundaries
+    w = torch.randn(x.shape, generator=g, dtype=torch.float64)
+    xc, cc = x.clone().requires_grad_(True), coef.clone().requires_grad_(True)
+    (O.lagrange1d(xc, cc, lo, hi, mesh, degree) * w).sum().backward()
+    xd = x.to(cuda_device, dtype).requires_grad_(True)
+    cd = coef.to(cuda_device, dtype).requires_grad_(True)
+    y = P.lagrange1d(xd, cd, lo, hi, mesh, degree)
+    (y * w.to(cuda_device, dtype)).sum().backward()
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    assert rel(y, O.lagrange1d(x, coef, lo, hi, mesh, degree)) < tol
+    assert rel(xd.grad, xc.grad) < tol * 10
+    assert rel(cd.grad, cc.grad) < tol * 10
+    y2 = P.lagrange1d(xd.detach().requires_grad_(True), cd.detach().requires_grad_(True), lo, hi, mesh, degree)
+    assert torch.equal(y2, y)
+    # interpolates its nodes exactly
+    nodes = torch.linspace(lo, hi, mesh * degree + 1, dtype=torch.float64)
+    yn = P.lagrange1d(nodes.to(cuda_device, dtype), coef.to(cuda_device, dtype), lo, hi, mesh, degree)
+    assert rel(yn, coef) < (1e-12 if dtype == torch.float64 else 1e-5)
+
+
+def test_single_nonlinear_module_matches_oracle(P, cuda_device):
+    """PDE-Net 1 model with the interpolated nonlinear source term (u_t = c lap(u) + f(u) shape)."""
+    dev = cuda_device
+    k, max_order, B, H, W, steps = 5, 2, 3, 26, 30, 3
+    dx, dt = 2 * math.pi / W, 2e-3
+    model = P.SingleNonLinear2d(k, max_order, dx, dt, nonlinear_interp_degree=2,
+                                nonlinear_interp_mesh_bound=(-1.5, 1.5), nonlinear_interp_mesh_size=6).to(dev)
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        for fd in [model.id] + model.fds:
+            fd.moment.add_(1e-2 * torch.randn(fd.moment.shape, generator=g, dtype=torch.float64).to(dev))
+            fd.x_proj()
+        model.coe.copy_(0.3 * torch.randn(model.coe.shape, generator=g, dtype=torch.float64))
+        model.nonlinearfitter.interp_coe.copy_(torch.sin(model.nonlinearfitter.nodes() * 2).cpu())
+    u0 = smooth_field(B, 1, H, W, 78)[:, 0]
+    w = torch.randn(u0.shape, generator=g, dtype=torch.float64)
+    out = model(u0.to(dev), steps)
+    (out * w.to(dev)).sum().backward()
+    # oracle on the same parameters
+    ks = model.scaled_kernels().detach().cpu()
+    K0, Ks = ks[0].clone().requires_grad_(True), ks[1:].clone().requires_grad_(True)
+    coe = model.coe.detach().cpu().clone().requires_grad_(True)
+    fc = model.nonlinearfitter.interp_coe.detach().cpu().clone().requires_grad_(True)
+    u = u0
+    for _ in range(steps):
+        u = O.single_nonlinear_step(u, K0, Ks, coe, fc, -1.5, 1.5, 6, 2, dt)
+    (u * w).sum().backward()
+    assert rel(out, u) < 1e-11
+    assert rel(model.coe.grad, coe.grad) < 1e-9
+    assert rel(model.nonlinearfitter.interp_coe.grad, fc.grad) < 1e-9
+
+
 def test_training_loss_closure_matches_oracle(P, cuda_device):
     """8f-3: data term + Huber-L1 sparsity of the SymNet and of the free moments, value and all
     parameter gradients against the oracle's closure."""
