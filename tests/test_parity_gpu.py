@@ -737,3 +737,33 @@ def test_errors(P, cuda_device):
         P.m2k(torch.zeros(1, 4, 4, dtype=torch.float64, device=cuda_device))
     assert _lib.lib().pdenet_supported(8, 7, 6, 2, 2) == 1
     assert _lib.lib().pdenet_supported(8, 9, 6, 2, 2) == 0
+
+
+def test_errors_of_the_feature_keeping_and_interpolation_entries(P, cuda_device):
+    """Raw C-ABI calls: NULL feature buffers and out-of-range interpolation settings are refused
+    with the documented codes, nothing is launched."""
+    import ctypes as C
+
+    from pdenet_b200 import _lib
+    dev = cuda_device
+    u = torch.zeros(1, 2, 8, 8, dtype=torch.float64, device=dev)
+    Ks = torch.zeros(6, 5, 5, dtype=torch.float64, device=dev)
+    sym = torch.zeros(2, P.symnet_param_count(12, 2), dtype=torch.float64, device=dev)
+    states = torch.empty(1, 1, 2, 8, 8, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib().pdenet_rollout_fwd_keep_f64(ptr(u), ptr(Ks), ptr(sym), ptr(states), None, 1, 2, 8, 8, 5, 6, 2, 1,
+                                                1e-3, st)
+    assert rc == _lib.E_BADARG
+    x = torch.zeros(10, dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.PdenetError) as e:      # degree 5 is not compiled
+        P.lagrange1d(x, torch.zeros(5 * 5 + 1, dtype=torch.float64, device=dev), 0.0, 1.0, 5, 5)
+    assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(_lib.PdenetError) as e:      # empty interval
+        P.lagrange1d(x, torch.zeros(11, dtype=torch.float64, device=dev), 1.0, 1.0, 5, 2)
+    assert e.value.code == _lib.E_BADARG
+    with pytest.raises(ValueError):                 # wrong number of node values
+        P.lagrange1d(x, torch.zeros(7, dtype=torch.float64, device=dev), 0.0, 1.0, 5, 2)
+    with pytest.raises(ValueError):                 # feature buffer of the wrong shape
+        P.slab_step(torch.zeros(1, 2, 8 + 4, 8, dtype=torch.float64, device=dev), Ks, sym, 2, 1e-3, 2,
+                    feats=torch.zeros(1, 12, 7, 8, dtype=torch.float64, device=dev))
