@@ -292,7 +292,8 @@ PDENET_API int pdenet_fma_peak(int elem_size, int iters, double *flops_out, floa
  * none shared with the neighbouring FMAs; 2 = one operand shared by 4 consecutive FMAs;
  * 3 / 4 = the filter-gradient kernel's register pattern (49 accumulators per thread, one
  * multiplicand shared by 7 consecutive FMAs, window rows re-read from shared memory) with two / one
- * grid columns per lane. */
+ * grid columns per lane; 5 = the same 49 accumulators with every operand already in registers and no
+ * ragged first / last window rows; 6 = variant 5 plus the per-row window loads from shared memory. */
 PDENET_API int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream);
 
 #ifdef __cplusplus

@@ -1069,6 +1069,46 @@ template <typename T, int VEC> __global__ void __launch_bounds__(192, 2) fgrad_p
   if (s == (T)123456789) out[0] = s;
 }
 
+// the same 49-accumulator pattern without shared-memory reads and without the ragged first / last
+// window rows: every pass touches all 49 accumulators (isolates the register-operand limit)
+template <typename T, bool LOADS> __global__ void __launch_bounds__(192, 2) fgrad_probe_dense_kernel(T *out, int iters) {
+  constexpr int K = 7;
+  __shared__ T sm[16 * 48];
+  for (int i = threadIdx.x; i < 16 * 48; i += blockDim.x) sm[i] = (T)0.999 + (T)i * (T)1e-6;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  T acc[K * K], gc[16], row[K + 1];
+#pragma unroll
+  for (int e = 0; e < K * K; ++e) acc[e] = T(0);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) gc[j] = (T)1e-3 * (T)(threadIdx.x + j);
+#pragma unroll
+  for (int x = 0; x < K + 1; ++x) row[x] = (T)0.999 + (T)x * (T)1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (LOADS) { // a fresh window row per pass, as the real kernel reads it (one value of the 8 is reused)
+#pragma unroll
+        for (int x = 0; x < K + 1; ++x) row[x] = sm[((r + it) & 15) * 48 + ((lane * 2 + x) & 47)];
+      }
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int bb = 0; bb < K; ++bb) acc[a * K + bb] = fma_(gc[(r + a) & 15], row[(r & 1) + bb], acc[a * K + bb]);
+    }
+    if (it == iters + 1) { // never true: keeps gc, row live as variables
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gc[j] += acc[j];
+#pragma unroll
+      for (int x = 0; x < K + 1; ++x) row[x] += acc[x];
+    }
+  }
+  T s = T(0);
+#pragma unroll
+  for (int e = 0; e < K * K; ++e) s += acc[e];
+  if (s == (T)123456789) out[0] = s;
+}
+
 } // namespace pdenet
 
 using namespace pdenet;
@@ -1437,7 +1477,7 @@ int pdenet_fma_peak(int elem_size, int iters, double *flops_out, float *ms_out, 
 }
 
 int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, float *ms_out, void *stream) {
-  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out || variant < 0 || variant > 4)
+  if ((elem_size != 4 && elem_size != 8) || iters <= 0 || !flops_out || !ms_out || variant < 0 || variant > 6)
     return PDENET_E_BADARG;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
@@ -1456,18 +1496,22 @@ int pdenet_fma_probe(int elem_size, int iters, int variant, double *flops_out, f
       if (variant == 2) fma_probe_kernel<double, 2><<<grid, block, 0, st>>>((double *)scratch, iters);
       if (variant == 3) fgrad_probe_kernel<double, 2><<<grid, block, 0, st>>>((double *)scratch, iters);
       if (variant == 4) fgrad_probe_kernel<double, 1><<<grid, block, 0, st>>>((double *)scratch, iters);
+      if (variant == 5) fgrad_probe_dense_kernel<double, false><<<grid, block, 0, st>>>((double *)scratch, iters);
+      if (variant == 6) fgrad_probe_dense_kernel<double, true><<<grid, block, 0, st>>>((double *)scratch, iters);
     } else {
       if (variant == 0) fma_peak_kernel<float><<<grid, block, 0, st>>>((float *)scratch, iters, 0.999f, 1e-3f);
       if (variant == 1) fma_probe_kernel<float, 1><<<grid, block, 0, st>>>((float *)scratch, iters);
       if (variant == 2) fma_probe_kernel<float, 2><<<grid, block, 0, st>>>((float *)scratch, iters);
       if (variant == 3) fgrad_probe_kernel<float, 2><<<grid, block, 0, st>>>((float *)scratch, iters);
       if (variant == 4) fgrad_probe_kernel<float, 1><<<grid, block, 0, st>>>((float *)scratch, iters);
+      if (variant == 5) fgrad_probe_dense_kernel<float, false><<<grid, block, 0, st>>>((float *)scratch, iters);
+      if (variant == 6) fgrad_probe_dense_kernel<float, true><<<grid, block, 0, st>>>((float *)scratch, iters);
     }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
   }
   cudaEventElapsedTime(ms_out, e0, e1);
-  *flops_out = 2.0 * (variant >= 3 ? 784 : 16 * 8) * (double)iters * (double)grid * block;
+  *flops_out = 2.0 * (variant >= 3 ? 784 : 16 * 8) * (double)iters * (double)grid * block; // variant 5: 16*49 = 784 too
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(scratch);

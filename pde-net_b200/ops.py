@@ -466,7 +466,8 @@ def fma_peak(dtype=torch.float64, iters: int = 4096, variant: int = 0):
     operand pattern (0: loop-invariant multiplicands, 1: three distinct register operands per FMA,
     2: one operand shared by four consecutive FMAs, 3 / 4: the filter-gradient kernel's pattern -- 49
     accumulators, one multiplicand shared by 7 FMAs, window rows from shared memory -- with two /
-    one columns per lane)."""
+    one columns per lane, 5: the same accumulators with all operands resident in registers, 6: variant 5
+    plus the per-row window loads from shared memory)."""
     flops, ms = C.c_double(0), C.c_float(0)
     _lib.check(_lib.lib().pdenet_fma_probe(8 if dtype == torch.float64 else 4, iters, variant, C.byref(flops),
                                            C.byref(ms), _stream()), "pdenet_fma_probe")
