@@ -526,6 +526,15 @@ def test_streamed_fwd_bwd_equals_resident(P, cuda_device):
     assert abs(loss.item() - ref_loss.item()) < 1e-12 * abs(ref_loss.item())
     for p, r in zip(model.parameters(), ref):
         assert rel(p.grad, r) < 1e-11
+    # the resident chunked pass of bench.py (ragged last chunk), features kept and recomputed
+    for keep in (True, False):
+        for p in model.parameters():
+            p.grad = None
+        model.keep_features = keep
+        loss = PP.chunked_fwd_bwd(model, u0.to(cuda_device), 3 * dt, scale, chunk=3)
+        assert abs(loss.item() - ref_loss.item()) < 1e-12 * abs(ref_loss.item())
+        for p, r in zip(model.parameters(), ref):
+            assert rel(p.grad, r) < 1e-11
 
 
 def test_cuda_graph_capture_small_config(P, cuda_device):
