@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the global batch (parity/debug only)")
     ap.add_argument("--size", type=int, default=0, help="override the grid side (debug only)")
     ap.add_argument("--blocks", type=int, default=0, help="override the number of dt-blocks (debug only)")
-    ap.add_argument("--chunk", type=int, default=16, help="trajectories per reverse-kernel launch")
+    ap.add_argument("--chunk", type=int, default=32, help="trajectories per reverse-kernel launch")
     ap.add_argument("--pass-chunk", type=int, default=32,
                     help="trajectories per forward+reverse rollout of the resident pass (0 = the whole shard)")
     ap.add_argument("--keep", choices=["on", "off"], default="on",
