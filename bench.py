@@ -285,7 +285,7 @@ def run_ours(args):
         return parallel.allreduce_gradients(params, loss=loss)
 
     # chunks of the streamed e2e pass: at least four per shard so the H2D copy overlaps compute
-    e2e_chunk = min(Bl, args.e2e_chunk if args.e2e_chunk > 0 else max(8, min(32, Bl // 4)))
+    e2e_chunk = min(Bl, args.e2e_chunk if args.e2e_chunk > 0 else max(8, min(32, Bl // 2)))
     e2e_bufs = [stage[:e2e_chunk], torch.empty_like(stage[:e2e_chunk])]
     copy_stream = torch.cuda.Stream(dev)
 
@@ -407,8 +407,9 @@ def run_ours(args):
                    "l2": "inputs (%.1f GB per pass) larger than L2; no flush needed" % (u0.numel() * 8 / 1e9)},
         "e2e": {"value": e2e, "unit": "grid-point-steps/s", "h2d_bytes_per_step": u0.numel() * u0.element_size(),
                 "d2h_bytes_per_step": (nparam + 1) * 8, "ms_per_step": ms_e2e / args.steps,
-                "how": "pinned host batch streamed in chunks of %d trajectories; H2D of chunk k+1 overlaps "
-                       "fwd+bwd of chunk k; loss+gradients copied back to pinned host memory" % e2e_chunk},
+                "how": "pinned host batch streamed in chunks of up to %d trajectories (first chunks smaller: %s); H2D of "
+                       "chunk k+1 overlaps fwd+bwd of chunk k; loss+gradients copied back to pinned host memory"
+                       % (e2e_chunk, parallel.ramp_chunks(Bl, e2e_chunk)[:3])},
         "gpu_launches": int(sum(kind_n.values())),
         "clocks": clocks,
         "roofline": {
@@ -453,7 +454,7 @@ def main():
     ap.add_argument("--keep", choices=["on", "off"], default="on",
                     help="keep the derivative features of each chunk for the reverse pass (off = recompute)")
     ap.add_argument("--e2e-chunk", type=int, default=0,
-                    help="trajectories per streamed chunk of the e2e pass (0 = shard/4, clamped to [8, 32])")
+                    help="largest streamed chunk of the e2e pass (0 = shard/2, clamped to [8, 32])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="f64 = the reference's precision (default)")
     args = ap.parse_args()

@@ -277,14 +277,32 @@ def chunked_fwd_bwd(model, u0: torch.Tensor, T: float, loss_scale: float, chunk:
     return total
 
 
+def ramp_chunks(B: int, chunk: int, first: int = 0):
+    """Chunk sizes for a streamed pass: a short first chunk (``first``, default chunk/4) so that the
+    one host-to-device copy nothing can overlap is short, a second chunk that completes the first
+    ``chunk`` trajectories, then full chunks."""
+    first = min(B, max(1, first or chunk // 4))
+    sizes, left = [first], B - first
+    if left > 0 and first < chunk:
+        n = min(chunk - first, left)
+        sizes.append(n)
+        left -= n
+    while left > 0:
+        n = min(chunk, left)
+        sizes.append(n)
+        left -= n
+    return sizes
+
+
 def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, chunk: int,
-                     bufs=None, copy_stream=None):
+                     bufs=None, copy_stream=None, ramp: bool = True):
     """End-to-end pass over a batch that lives in PINNED HOST memory: trajectories are independent,
     so the batch is streamed through the device in chunks -- the host-to-device copy of chunk k+1
     (on a side stream) overlaps the fused forward + reverse rollout of chunk k, and the parameter
-    gradients accumulate in ``.grad``.  Loss = ``loss_scale * sum(final_state**2)`` summed over
-    chunks (``loss_scale = 1/numel`` gives the mean square).  Returns the summed loss (0-dim
-    device tensor)."""
+    gradients accumulate in ``.grad``.  With ``ramp`` the first chunks are smaller (chunk/4, chunk/2,
+    then ``chunk``): only the very first copy cannot be overlapped.  Loss =
+    ``loss_scale * sum(final_state**2)`` summed over chunks (``loss_scale = 1/numel`` gives the mean
+    square).  Returns the summed loss (0-dim device tensor)."""
     dev = next(model.parameters()).device
     B = host_u0.shape[0]
     main = torch.cuda.current_stream(dev)
@@ -295,25 +313,24 @@ def streamed_fwd_bwd(model, host_u0: torch.Tensor, T: float, loss_scale: float, 
     copied = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     total = torch.zeros((), dtype=host_u0.dtype, device=dev)
-    starts = list(range(0, B, chunk))
+    sizes = ramp_chunks(B, chunk) if ramp else ramp_chunks(B, chunk, chunk)
+    starts = [sum(sizes[:i]) for i in range(len(sizes))]
 
     def issue_copy(k):
-        b0 = starts[k]
-        nb = min(chunk, B - b0)
+        b0, nb = starts[k], sizes[k]
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(freed[k % 2])     # chunk k-2 has finished with this buffer
             bufs[k % 2][:nb].copy_(host_u0[b0:b0 + nb], non_blocking=True)
             copied[k % 2].record(copy_stream)
-        return nb
 
     copy_stream.wait_stream(main)
-    nbs = {0: issue_copy(0)}
+    issue_copy(0)
     for k in range(len(starts)):
         if k + 1 < len(starts):
-            nbs[k + 1] = issue_copy(k + 1)
+            issue_copy(k + 1)
         main.wait_event(copied[k % 2])
-        out = model(bufs[k % 2][:nbs[k]], T)
+        out = model(bufs[k % 2][:sizes[k]], T)
         loss = out.square().sum() * loss_scale
         loss.backward()
         total = total + loss.detach()
