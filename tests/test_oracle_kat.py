@@ -223,3 +223,72 @@ def test_kat8_lagrange1d_reproduces_polynomials_and_nodes(degree):
     left = O.lagrange1d(edges - 1e-9, coef, lo, hi, mesh, degree)
     right = O.lagrange1d(edges + 1e-9, coef, lo, hi, mesh, degree)
     assert (left - right).abs().max() < 1e-6
+
+
+# ----------------------------------------------------------------------------- property tests
+# (hypothesis; small random configurations -- the size-independent properties the domain offers)
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(k=st.sampled_from([3, 5, 7]), max_order=st.integers(1, 2), C=st.integers(1, 2), L=st.integers(0, 3),
+       H=st.integers(1, 12), W=st.integers(1, 12), sy=st.integers(-15, 15), sx=st.integers(-15, 15),
+       seed=st.integers(0, 10 ** 6))
+def test_property_shift_equivariance_any_shape(k, max_order, C, L, H, W, sy, sx, seed):
+    """Periodic boundaries: rolling the input rolls the output, for any grid (also grids smaller
+    than the stencil, where taps wrap several times), any depth, any shift."""
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(max_order)
+    N = len(orders)
+    Ks = torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    sym = 0.3 * torch.randn(C, O.symnet_param_count(C * N, L), generator=g, dtype=torch.float64)
+    u = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    a = O.rollout(torch.roll(u, (sy, sx), (2, 3)), Ks, sym, L, 1e-2, 2)[-1]
+    b = torch.roll(O.rollout(u, Ks, sym, L, 1e-2, 2)[-1], (sy, sx), (2, 3))
+    assert torch.allclose(a, b, rtol=1e-12, atol=1e-12)
+
+
+@settings(max_examples=25, deadline=None)
+@given(k=st.sampled_from([3, 5]), N=st.integers(1, 5), H=st.integers(2, 10), W=st.integers(2, 10),
+       alpha=st.floats(-2, 2), beta=st.floats(-2, 2), seed=st.integers(0, 10 ** 6))
+def test_property_linear_model_superposition(k, N, H, W, alpha, beta, seed):
+    """Row a12 is linear in the state: rollout(alpha u + beta v) = alpha rollout(u) + beta rollout(v)."""
+    g = torch.Generator().manual_seed(seed)
+    K0 = torch.randn(k, k, generator=g, dtype=torch.float64) * 0.1
+    Ks = torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    coe = torch.randn(N, H, W, generator=g, dtype=torch.float64)
+    u, v = (torch.randn(2, H, W, generator=g, dtype=torch.float64) for _ in range(2))
+    lhs = O.linear_rollout(alpha * u + beta * v, K0, Ks, coe, 1e-2, 3)[-1]
+    rhs = alpha * O.linear_rollout(u, K0, Ks, coe, 1e-2, 3)[-1] + beta * O.linear_rollout(v, K0, Ks, coe, 1e-2, 3)[-1]
+    assert torch.allclose(lhs, rhs, rtol=1e-11, atol=1e-11)
+
+
+@settings(max_examples=20, deadline=None)
+@given(k=st.sampled_from([3, 5, 7]), seed=st.integers(0, 10 ** 6))
+def test_property_m2k_k2m_inverse_and_linear(k, seed):
+    g = torch.Generator().manual_seed(seed)
+    M1, M2 = (torch.randn(3, k, k, generator=g, dtype=torch.float64) for _ in range(2))
+    assert torch.allclose(O.k2m(O.m2k(M1)), M1, rtol=1e-8, atol=1e-9)
+    assert torch.allclose(O.m2k(2.0 * M1 - 0.5 * M2), 2.0 * O.m2k(M1) - 0.5 * O.m2k(M2), rtol=1e-10, atol=1e-10)
+
+
+@settings(max_examples=15, deadline=None)
+@given(k=st.sampled_from([3, 5]), C=st.integers(1, 2), L=st.integers(0, 2), H=st.integers(3, 9), W=st.integers(3, 9),
+       steps=st.integers(1, 3), seed=st.integers(0, 10 ** 6))
+def test_property_torch_and_numpy_oracles_agree(k, C, L, H, W, steps, seed):
+    """Two independent restatements (autograd vs hand-derived adjoint) give the same states and the
+    same input gradient on random small configurations."""
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(1)
+    N = len(orders)
+    Ks = torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    sym = 0.3 * torch.randn(C, O.symnet_param_count(C * N, L), generator=g, dtype=torch.float64)
+    u0 = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    uc = u0.clone().requires_grad_(True)
+    last = O.rollout(uc, Ks, sym, L, 1e-2, steps)[-1]
+    (last * w).sum().backward()
+    out = ONP.rollout_fwd_bwd(u0.numpy(), Ks.numpy(), sym.numpy(), L, 1e-2, steps, w.numpy())
+    states, gu = out[0], out[1]
+    assert np.allclose(states[-1], last.detach().numpy(), rtol=1e-11, atol=1e-12)
+    assert np.allclose(gu, uc.grad.numpy(), rtol=1e-9, atol=1e-11)

@@ -776,3 +776,43 @@ def test_errors_of_the_feature_keeping_and_interpolation_entries(P, cuda_device)
     with pytest.raises(ValueError):                 # feature buffer of the wrong shape
         P.slab_step(torch.zeros(1, 2, 8 + 4, 8, dtype=torch.float64, device=dev), Ks, sym, 2, 1e-3, 2,
                     feats=torch.zeros(1, 12, 7, 8, dtype=torch.float64, device=dev))
+
+
+# ------------------------------------------------------------------ randomised parity (hypothesis)
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_BANKS = [(1, 1), (1, 2), (1, 3), (2, 1), (2, 2), (2, 3), (3, 1), (4, 1)]   # (max_order, C) that are compiled
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(k=st.sampled_from([3, 5, 7]), bank=st.sampled_from(_BANKS), L=st.integers(0, 4), B=st.integers(1, 3),
+       H=st.integers(1, 40), W=st.integers(1, 70), steps=st.integers(1, 3), keep=st.booleans(),
+       chunk=st.integers(0, 3), grad_all=st.booleans(), seed=st.integers(0, 10 ** 6))
+def test_property_cuda_rollout_matches_oracle(P, cuda_device, k, bank, L, B, H, W, steps, keep, chunk, grad_all, seed):
+    """Random shapes (ragged tiles, grids smaller than the stencil, odd widths), banks, depths,
+    chunkings and both reverse paths: states and all gradients within 1e-10 per step of the oracle."""
+    max_order, C = bank
+    dev = cuda_device
+    orders, M, scales, sym = make_model(k, max_order, C, L, 0.3, seed)
+    Ks = O.scaled_kernels(M, scales)
+    u0 = smooth_field(B, C, H, W, seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    w = torch.randn(steps, B, C, H, W, generator=g, dtype=torch.float64)
+    if not grad_all:
+        w[:-1] = 0
+    uc, Kc, sc = u0.clone().requires_grad_(True), Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    ref = torch.stack(O.rollout(uc, Kc, sc, L, 1e-2, steps))
+    (ref * w).sum().backward()
+    ud, Kd, sd = [t.to(dev).requires_grad_(True) for t in (u0, Ks, sym)]
+    if grad_all:
+        st_ = P.rollout(ud, Kd, sd, L, 1e-2, steps, batch_chunk=chunk, keep_features=keep)
+        (st_ * w.to(dev)).sum().backward()
+    else:
+        st_ = P.rollout(ud, Kd, sd, L, 1e-2, steps, last_only=True, batch_chunk=chunk, keep_features=keep)[None]
+        (st_[0] * w[-1].to(dev)).sum().backward()
+        ref = ref[-1:]
+    tol = 1e-10 * steps
+    assert rel(st_, ref) < tol
+    assert rel(ud.grad, uc.grad) < tol
+    assert rel(Kd.grad, Kc.grad) < tol
+    assert rel(sd.grad, sc.grad) < tol
