@@ -334,12 +334,16 @@ def run_ours(args):
     ops.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         one_pass(u0)
+        marks[i + 1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))  # this rank's passes
     kind_ms, kind_n = ops.profile_read()
     ops.profile_enable(False)
     # ---- timed region 2: end to end (pinned host inputs -> device, loss+grads -> host)
@@ -398,6 +402,7 @@ def run_ours(args):
     line = {
         "metric": "grid-point-steps/sec fwd+bwd rollout", "value": value, "unit": "grid-point-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "ms_per_step_best": per_step[0], "ms_per_step_median": statistics.median(per_step),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": CFG["workload"] if args.dtype == "f64" else CFG["workload"].replace("fp64", "fp32"),
                    "global_batch": B, "per_gpu_batch": Bl, "grid": [H, W],
