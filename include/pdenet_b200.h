@@ -56,6 +56,11 @@ PDENET_API const char *pdenet_error_string(int code);
 PDENET_API int pdenet_supported(int elem_size, int k, int N, int C, int L);
 /* number of SymNet scalars per output channel: sum_{i<L}(2(m+i)+2) + (m+L) + 1 */
 PDENET_API int pdenet_symnet_param_count(int m, int L);
+/* 1 if the recomputing reverse rollout (pdenet_rollout_bwd_*) does not fit this bank in shared
+ * memory (3-channel banks with deep SymNets in fp64) and returns PDENET_E_UNSUPPORTED, so that the
+ * feature-keeping pair (pdenet_rollout_fwd_keep_* / pdenet_rollout_bwd_kept_*) must be used;
+ * 0 if both work; -1 if the combination is not supported at all. */
+PDENET_API int pdenet_rollout_bwd_needs_features(int elem_size, int k, int N, int C, int L);
 
 /* ---- rows a1-a3: moment <-> kernel map (upstream aTEAM MK.py::_MK/M2K/K2M) -----------------
  * kernels[n] = scale[n] * A^-1 . moments[n] . A^-T,  A[i,j] = (j-(k-1)/2)^i / i!.

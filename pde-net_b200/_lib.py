@@ -30,6 +30,7 @@ _PROTOS = {
     "pdenet_fd2d_bwd_workspace_bytes": (_sz, [_i, _i]),
     "pdenet_fd2d_bwd_{t}": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_vp]),
     "pdenet_rollout_fwd_{t}": (_i, [_vp] * 4 + [_i] * 8 + [_d, _vp]),
+    "pdenet_rollout_bwd_needs_features": (_i, [_i] * 5),
     "pdenet_rollout_fwd_keep_{t}": (_i, [_vp] * 5 + [_i] * 8 + [_d, _vp]),
     "pdenet_rollout_bwd_kept_{t}": (_i, [_vp, _vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
     "pdenet_rollout_bwd_workspace_bytes": (_sz, [_i] * 9),

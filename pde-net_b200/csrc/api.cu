@@ -52,6 +52,7 @@ struct ProfScope {
   extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
   extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, cudaStream_t);                          \
   extern template int upload_taps<TT, KK>(int, int, const TT *, int, cudaStream_t);                              \
+  extern template size_t step_smem_bytes<TT, KK>(int, int, int, int);                                            \
   extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, cudaStream_t);                    \
   extern template void filter_grad_tile<TT, KK>(int &, int &);                                                   \
   extern template int adjoint_vlb<TT, KK>();                                                                     \
@@ -144,7 +145,8 @@ static bool lin_supported(int NF) {
 }
 // vector length of the SymNet-gradient warp reduction: needs M + L + 1 <= VL
 static int pick_vl(int M, int L) {
-  if (M + L + 1 <= 16) return 16;
+  // the 16-long gradient vectors are only instantiated for banks with M + 1 < 16 features (inst.cu)
+  if (M + L + 1 <= 16 && M + 1 < 16) return 16;
   if (M + L + 1 <= 32) return 32;
   return 0;
 }
@@ -1143,6 +1145,18 @@ int pdenet_supported(int elem_size, int k, int N, int C, int L) {
 }
 
 int pdenet_symnet_param_count(int m, int L) { return symnet_param_count(m, L); }
+
+int pdenet_rollout_bwd_needs_features(int elem_size, int k, int N, int C, int L) {
+  if (!pdenet_supported(elem_size, k, N, C, L)) return -1;
+  const int Psym = symnet_param_count(N * C, L);
+  size_t smem = 0;
+  if (elem_size == 8) {
+    PDENET_DISPATCH_K(k, smem = (step_smem_bytes<double, KK_>(MODE_BWD_A, N, C, Psym)));
+  } else {
+    PDENET_DISPATCH_K(k, smem = (step_smem_bytes<float, KK_>(MODE_BWD_A, N, C, Psym)));
+  }
+  return smem > (size_t)227 * 1024 ? 1 : 0;
+}
 
 int pdenet_m2k_f64(const double *m, const double *s, double *kout, int N, int k, void *st) {
   return sandwich<double>(SW_M2K, m, s, nullptr, kout, N, k, st);

@@ -16,6 +16,8 @@ template <typename KernelT> static int allow_smem(KernelT kern, size_t smem) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 0 : -4;
 }
 
+constexpr size_t kMaxDynamicSmem = 227 * 1024;
+
 template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1>
 static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
   using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
@@ -26,6 +28,7 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   const int grid = p.n_items < sms ? p.n_items : sms;
   constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT;
   const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);
+  if (smem > kMaxDynamicSmem) return -2; // e.g. 3-channel banks with deep SymNets in the recomputing reverse kernel
   auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
@@ -68,6 +71,16 @@ int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms,
   return -2;
 }
 
+template <typename T, int K> size_t step_smem_bytes(int mode, int N, int C, int Psym) {
+  const bool rev = mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT;
+#define PDENET_CASE(NN, CC)                                                                                       \
+  if (N == NN && C == CC)                                                                                        \
+    return StepCfg<T, K, NN, CC, step_threads(MODE_BWD_A, NN * CC)>::smem_bytes(Psym, rev, mode == MODE_BWD_A_KEPT);
+  PDENET_FOR_NC(PDENET_CASE)
+#undef PDENET_CASE
+  return 0;
+}
+
 template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st) {
   using Cfg = AdjCfg<T, K>;
   const size_t smem = Cfg::smem_bytes(p.N);
@@ -108,6 +121,7 @@ template <typename T, int K> void adjoint_tile(int &tw, int &th) {
 }
 
 template int launch_step<PDENET_T, PDENET_K>(int, int, int, int, const StepParams<PDENET_T> &, int, cudaStream_t);
+template size_t step_smem_bytes<PDENET_T, PDENET_K>(int, int, int, int);
 template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int, cudaStream_t);
 template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, cudaStream_t);
 template void filter_grad_tile<PDENET_T, PDENET_K>(int &, int &);

@@ -15,6 +15,8 @@ namespace pdenet {
 template <typename T, int K>
 int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st);
 template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st);
+// dynamic shared memory (bytes) a step kernel of this bank needs in `mode`; 0 if the bank is not compiled
+template <typename T, int K> size_t step_smem_bytes(int mode, int N, int C, int Psym);
 template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st);
 template <typename T, int K> void filter_grad_tile(int &tw, int &th);
 template <typename T, int K> int adjoint_vlb();

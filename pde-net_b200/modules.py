@@ -92,8 +92,8 @@ class FD2d(nn.Module):
 
     def x_proj(self, *args, **kw):
         """Re-impose the pinned moment entries (sum-rule constraint) after an optimiser update."""
-        with torch.no_grad():
-            self.moment.data = torch.where(self._pinned, self._init.to(self.moment.dtype), self.moment.data)
+        with torch.no_grad():  # in place: captured CUDA graphs keep reading the same storage
+            self.moment.copy_(torch.where(self._pinned, self._init.to(self.moment.dtype), self.moment))
 
     def grad_proj(self, *args, **kw):
         """Zero the gradient of pinned moment entries."""

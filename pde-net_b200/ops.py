@@ -168,7 +168,10 @@ class _Rollout(torch.autograd.Function):
         feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
         auto = keep_features is None
         if auto:
-            keep_features = feat_bytes <= FEATURE_CACHE_BYTES
+            # a few banks (3 channels, deep SymNet, fp64) only fit the reverse pass with kept features
+            needs = _lib.lib().pdenet_rollout_bwd_needs_features(u0.element_size(), k, N, Cc, L) == 1
+            keep_features = needs or feat_bytes <= FEATURE_CACHE_BYTES
+            auto = not needs
         keep_features = bool(keep_features) and any(ctx.needs_input_grad[:3])
         feats = None
         if keep_features:
