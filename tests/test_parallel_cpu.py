@@ -149,3 +149,23 @@ def test_shard_range_and_single_rank_slab():
     slab = PP.SlabDecomposition(u0.shape[2], 2, 0, 1)
     fin = slab.rollout(u0, Ks, sym, 2, 1e-2, 2, step_fn=_oracle_slab_step)
     assert torch.allclose(fin, O.rollout(u0, Ks, sym, 2, 1e-2, 2)[-1], rtol=1e-12, atol=1e-13)
+
+
+def test_ramp_chunks_cover_the_batch_exactly():
+    """Chunk schedule of the streamed e2e pass: short first chunk, the second completes the first
+    full chunk, every size within bounds, sizes add up to the batch (host logic, no GPU)."""
+    import importlib.util
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pde-net_b200",
+                            "parallel.py")).read()
+    ns = {}
+    exec(re.search(r"def ramp_chunks.*?return sizes\n", src, re.S).group(0), ns)
+    ramp = ns["ramp_chunks"]
+    assert ramp(256, 32) == [8, 24] + [32] * 7
+    assert ramp(32, 16) == [4, 12, 16]
+    assert ramp(7, 3, 3) == [3, 3, 1]
+    for B in range(1, 80):
+        for chunk in range(1, 40):
+            sizes = ramp(B, chunk)
+            assert sum(sizes) == B and all(1 <= s <= max(chunk, 1) for s in sizes)
+            assert sizes[0] <= max(1, chunk // 4) or B < chunk // 4 or chunk < 4
