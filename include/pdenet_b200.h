@@ -17,8 +17,14 @@
  *   - feature index fed to SymNet: f = c*N + n;
  *   - SymNet flat layout per output channel (Psym scalars): for i < L: W_i[2, m+i] row-major,
  *     b_i[2]; then w_f[m+L], b_f[1];  m = C*N;
- *   - the callee allocates nothing and keeps no global state; all work is ordered on `stream`
- *     (a cudaStream_t passed as void*); reductions are deterministic (fixed order);
+ *   - the callee allocates nothing (outputs and workspaces are the caller's); all work is ordered
+ *     on `stream` (a cudaStream_t passed as void*); reductions are deterministic (fixed order);
+ *   - the only cross-call state is a ring of 8 constant-memory slots per device that hold a
+ *     call's filter taps: a call takes the next slot, makes `stream` wait (event) for the slot's
+ *     previous user and releases it after its last kernel, so calls may be issued concurrently
+ *     from several host threads / streams.  Inside a CUDA-graph capture the events are not used:
+ *     a captured graph is self-consistent, but do not replay it concurrently with other calls
+ *     into this library on other streams of the same device;
  *   - return value 0 = success, negative = PDENET_E_* below.  No exceptions cross the boundary.
  */
 #ifndef PDENET_B200_H_
