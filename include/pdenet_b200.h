@@ -20,9 +20,11 @@
  *   - the callee allocates nothing (outputs and workspaces are the caller's); all work is ordered
  *     on `stream` (a cudaStream_t passed as void*); reductions are deterministic (fixed order);
  *   - the only cross-call state is a ring of 8 constant-memory slots per device that hold a
- *     call's filter taps: a call takes the next slot, makes `stream` wait (event) for the slot's
- *     previous user and releases it after its last kernel, so calls may be issued concurrently
- *     from several host threads / streams.  Inside a CUDA-graph capture the events are not used:
+ *     call's filter taps: a call LEASES a free slot for the whole time it is enqueuing work (a
+ *     ninth concurrent caller blocks until one is returned), makes `stream` wait (event) for the
+ *     slot's previous user and records the slot's release event after its last kernel, so calls
+ *     may be issued concurrently from several host threads / streams; the launch counters of the
+ *     measurement hooks are atomic.  Inside a CUDA-graph capture the events are not used:
  *     a captured graph is self-consistent, but do not replay it concurrently with other calls
  *     into this library on other streams of the same device;
  *   - return value 0 = success, negative = PDENET_E_* below.  No exceptions cross the boundary.
@@ -56,7 +58,10 @@ extern "C" {
 #define PDENET_GRAD_LAST 0 /* grad_states is [B,C,H,W]: dLoss/d(state after the last step) */
 #define PDENET_GRAD_ALL 1  /* grad_states is [steps,B,C,H,W]: one seed per step            */
 
+/* C-ABI revision (bumped with every signature change; the bindings refuse a mismatching binary) and
+ * the content hash of the sources the binary was built from (pde-net_b200/build.py). */
 PDENET_API int pdenet_version(void);
+PDENET_API const char *pdenet_build_id(void);
 PDENET_API const char *pdenet_error_string(int code);
 /* 1 if rollout kernels were compiled for (elem_size 4|8, k, N, C); L only needs L<=MAX_LAYERS */
 PDENET_API int pdenet_supported(int elem_size, int k, int N, int C, int L);
@@ -108,6 +113,22 @@ PDENET_API int pdenet_rollout_fwd_f64(const double *u0, const double *kernels, c
                            int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
 PDENET_API int pdenet_rollout_fwd_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B, int C,
                            int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+
+/* ---- row a8: the right-hand side itself (upstream polypde.py::POLYPDE2D.RightHandItems) -----
+ * out[b,c] = SymNet_c(FD2d(u)[b]) = F(u), no Euler update (the same fused kernel, one launch).
+ * pdenet_rhs_bwd_*: given dLoss/dF returns dLoss/du (may be NULL), dLoss/dkernels (may be NULL) and
+ * dLoss/dsymnet (may be NULL); workspace as for pdenet_rollout_bwd_* (same size function). */
+PDENET_API int pdenet_rhs_fwd_f64(const double *u, const double *kernels, const double *symnet, double *out, int B, int C,
+                       int H, int W, int k, int N, int L, void *stream);
+PDENET_API int pdenet_rhs_fwd_f32(const float *u, const float *kernels, const float *symnet, float *out, int B, int C, int H,
+                       int W, int k, int N, int L, void *stream);
+PDENET_API int pdenet_rhs_bwd_f64(const double *u, const double *grad_out, const double *kernels, const double *symnet,
+                       double *grad_u, double *grad_kernels, double *grad_symnet, void *workspace,
+                       size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                       void *stream);
+PDENET_API int pdenet_rhs_bwd_f32(const float *u, const float *grad_out, const float *kernels, const float *symnet,
+                       float *grad_u, float *grad_kernels, float *grad_symnet, void *workspace, size_t workspace_bytes,
+                       int batch_chunk, int B, int C, int H, int W, int k, int N, int L, void *stream);
 
 /* ---- row a11: reverse rollout -------------------------------------------------------------
  * Recomputes stencils + SymNet from the stored states; returns dLoss/du0 [B,C,H,W] (may be

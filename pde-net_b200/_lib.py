@@ -20,6 +20,7 @@ _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 # name -> (restype, argtypes); "{t}" expands to f64 / f32
 _PROTOS = {
     "pdenet_version": (_i, []),
+    "pdenet_build_id": (C.c_char_p, []),
     "pdenet_error_string": (C.c_char_p, [_i]),
     "pdenet_supported": (_i, [_i] * 5),
     "pdenet_symnet_param_count": (_i, [_i, _i]),
@@ -31,6 +32,8 @@ _PROTOS = {
     "pdenet_fd2d_bwd_{t}": (_i, [_vp] * 6 + [_sz] + [_i] * 6 + [_vp]),
     "pdenet_rollout_fwd_{t}": (_i, [_vp] * 4 + [_i] * 8 + [_d, _vp]),
     "pdenet_rollout_bwd_needs_features": (_i, [_i] * 5),
+    "pdenet_rhs_fwd_{t}": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
+    "pdenet_rhs_bwd_{t}": (_i, [_vp] * 8 + [_sz] + [_i] * 8 + [_vp]),
     "pdenet_rollout_fwd_keep_{t}": (_i, [_vp] * 5 + [_i] * 8 + [_d, _vp]),
     "pdenet_rollout_bwd_kept_{t}": (_i, [_vp, _vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
     "pdenet_rollout_bwd_workspace_bytes": (_sz, [_i] * 9),
@@ -72,22 +75,40 @@ def exported_symbols():
 _lib = None
 
 
+#: C-ABI revision this binding was written against (``pdenet_version()``); bumped with every
+#: signature change so that a stale binary is refused instead of being called with shifted arguments
+ABI_VERSION = 200
+
+
+def _build_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pdenet_b200_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def lib() -> C.CDLL:
+    """Load (building or re-building first if the binary is missing or stale) and bind the library."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        build = _build_module()
+        if not build.up_to_date():
             # not a fallback: compile the CUDA library in place (nvcc, sm_100a) or fail loudly
             try:
-                import importlib.util
-                spec = importlib.util.spec_from_file_location("pdenet_b200_build", os.path.join(_HERE, "build.py"))
-                mod = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(mod)
-                mod.build()
+                build.build()
             except Exception as e:  # noqa: BLE001
                 raise RuntimeError(
-                    "pdenet_b200: %s is missing and could not be built (%s) -- build it with "
+                    "pdenet_b200: %s is missing or stale and could not be built (%s) -- build it with "
                     "`python pde-net_b200/build.py` (there is no CPU fallback)" % (LIB_PATH, e)) from e
         l = C.CDLL(LIB_PATH)
+        l.pdenet_version.restype = _i
+        l.pdenet_build_id.restype = C.c_char_p
+        if l.pdenet_version() != ABI_VERSION or l.pdenet_build_id().decode() != build.source_hash():
+            raise RuntimeError("pdenet_b200: %s was built from other sources (ABI %d, build id %s; expected %d, %s) "
+                               "-- rebuild with `python pde-net_b200/build.py --force`"
+                               % (LIB_PATH, l.pdenet_version(), l.pdenet_build_id().decode(), ABI_VERSION,
+                                  build.source_hash()))
         for name, (res, args) in _PROTOS.items():
             for n in ([name.format(t="f64"), name.format(t="f32")] if "{t}" in name else [name]):
                 fn = getattr(l, n)

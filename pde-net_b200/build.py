@@ -25,15 +25,33 @@ KS = [3, 5, 7]
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
         os.path.join(HERE, "..", "include", "pdenet_b200.h")]
 
 
+ID_FILE = os.path.join(OBJ, "build_id.txt")
+
+
+def source_hash() -> str:
+    """Content hash of every source the library is built from (csrc/* and the C-ABI header).  It is
+    compiled into the library (``pdenet_build_id()``) and checked by ``_lib.lib()``, so a stale binary
+    is rebuilt or refused instead of being called with a mismatching ABI."""
+    import hashlib
+    h = hashlib.sha256()
+    for src in _sources():
+        if os.path.isfile(src):
+            h.update(os.path.basename(src).encode())
+            h.update(open(src, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+    """True if the shared object exists and was built from the present sources (content hash, not
+    mtimes: the tree is copied to the GPU box without them)."""
+    if not os.path.exists(LIB) or not os.path.exists(ID_FILE):
         return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(s) <= t for s in _sources())
+    return open(ID_FILE).read().strip() == source_hash()
 
 
 def _run(cmd):
@@ -48,6 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
+    build_id = source_hash()
     jobs = []
     for tname, ctype in TYPES:
         for k in KS:
@@ -55,12 +74,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             jobs.append((o, [nvcc, *NVCC_FLAGS, f"-DPDENET_T={ctype}", f"-DPDENET_K={k}", "-c",
                              os.path.join(CSRC, "inst.cu"), "-o", o]))
     o = os.path.join(OBJ, "api.o")
-    jobs.append((o, [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "api.cu"), "-o", o]))
+    jobs.append((o, [nvcc, *NVCC_FLAGS, '-DPDENET_BUILD_ID="%s"' % build_id, "-c", os.path.join(CSRC, "api.cu"),
+                     "-o", o]))
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):
             if verbose and out.strip():
                 print(out)
     _run([nvcc, "-shared", "-o", LIB, *[j[0] for j in jobs], "-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(ID_FILE, "w") as f:
+        f.write(build_id + "\n")
     return LIB
 
 

@@ -289,6 +289,24 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
   T kacc[VLB];
 #pragma unroll
   for (int e = 0; e < VLB; ++e) kacc[e] = T(0);
+  double *slot = p.dk_partial + ((size_t)(blockIdx.x * (NTHREADS / 32) + part) * N + n) * VLB;
+  // fp32: the per-lane accumulators are widened once per ITEM (<= MT*RW*VEC products each in single
+  // precision), the cross-lane sum and everything after it run in double -- the error of the filter
+  // gradient then no longer grows with the grid size or the batch.  fp64 reduces once per launch.
+  auto flush_f32 = [&]() {
+#pragma unroll
+    for (int c0 = 0; c0 < VLB; c0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = (double)kacc[c0 + i];
+        kacc[c0 + i] = T(0);
+      }
+      warp_reduce_vec<double, 16>(v); // v[0] = element lane/2, duplicated over two lanes
+      const int e = c0 + (lane >> 1);
+      if ((lane & 1) == 0 && e < KK) slot[e] += v[0];
+    }
+  };
 
   int item = blockIdx.x, ub = 0;
   if (item < p.n_items) stage_u(item, 0);
@@ -370,13 +388,13 @@ __global__ void __launch_bounds__(FGradCfg<T, K>::NT, 2) filter_grad_kernel(cons
         }
       }
     }
+    if constexpr (sizeof(T) == 4) flush_f32();
     ub ^= 1;
   }
   cp_async_wait<0>();
 
-  {
+  if constexpr (sizeof(T) == 8) {
     warp_reduce_vec<T, VLB>(kacc);
-    double *slot = p.dk_partial + ((size_t)(blockIdx.x * (NTHREADS / 32) + part) * N + n) * VLB;
     if constexpr (VLB >= 32) {
 #pragma unroll
       for (int i = 0; i < VLB / 32; ++i) {

@@ -4,7 +4,9 @@
 #include "launch.cuh"
 #include "small_kernels.cuh"
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -19,9 +21,13 @@ struct ProfRec {
   cudaEvent_t e0, e1;
 };
 struct Prof {
-  bool on = false;
-  long long launches[PDENET_PROF_KINDS] = {0, 0, 0, 0, 0};
+  std::atomic<bool> on{false};
+  std::atomic<long long> launches[PDENET_PROF_KINDS];
+  std::mutex m; // guards recs
   std::vector<ProfRec> recs;
+  Prof() {
+    for (auto &l : launches) l.store(0);
+  }
 };
 static Prof g_prof;
 
@@ -29,8 +35,8 @@ struct ProfScope {
   ProfRec r;
   cudaStream_t st;
   bool live;
-  ProfScope(int kind, cudaStream_t s) : st(s), live(g_prof.on) {
-    g_prof.launches[kind]++;
+  ProfScope(int kind, cudaStream_t s) : st(s), live(g_prof.on.load(std::memory_order_relaxed)) {
+    g_prof.launches[kind].fetch_add(1, std::memory_order_relaxed);
     r.kind = kind;
     if (live) {
       cudaEventCreate(&r.e0);
@@ -41,6 +47,7 @@ struct ProfScope {
   ~ProfScope() {
     if (live) {
       cudaEventRecord(r.e1, st);
+      std::lock_guard<std::mutex> lk(g_prof.m);
       g_prof.recs.push_back(r);
     }
   }
@@ -68,24 +75,40 @@ PDENET_EXTERN(float, 3) PDENET_EXTERN(float, 5) PDENET_EXTERN(float, 7)
 // after its last kernel.  This is the library's only cross-call state.
 struct SlotRing {
   std::mutex m;
-  int next = 0;
+  std::condition_variable cv;
+  int next[16] = {0};
+  bool leased[16][kConstSlots] = {{false}};
   cudaEvent_t ev[16][kConstSlots];
   bool have[16] = {false};
 };
 static SlotRing g_slots;
 
+// A lease covers the whole host-side enqueue of a call: the slot is marked `leased` under the
+// mutex until the destructor has recorded the slot's release event, so a concurrent call on another
+// host thread can never pick a slot whose owner is still enqueuing kernels (it takes the next free
+// slot, or blocks on the condition variable if all eight are out).  Device-side ordering between
+// consecutive users of a slot is the event: the new user's stream waits for the previous user's
+// last kernel before its upload overwrites the taps.
 struct SlotLease {
   int slot = -1, dev = 0;
   cudaStream_t st;
   explicit SlotLease(cudaStream_t s) : st(s) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return;
-    std::lock_guard<std::mutex> lk(g_slots.m);
+    std::unique_lock<std::mutex> lk(g_slots.m);
     if (!g_slots.have[dev]) {
       for (int i = 0; i < kConstSlots; ++i) cudaEventCreateWithFlags(&g_slots.ev[dev][i], cudaEventDisableTiming);
       g_slots.have[dev] = true;
     }
-    slot = g_slots.next;
-    g_slots.next = (g_slots.next + 1) % kConstSlots;
+    for (;;) {
+      for (int i = 0; i < kConstSlots && slot < 0; ++i) {
+        const int c = (g_slots.next[dev] + i) % kConstSlots;
+        if (!g_slots.leased[dev][c]) slot = c;
+      }
+      if (slot >= 0) break;
+      g_slots.cv.wait(lk);
+    }
+    g_slots.leased[dev][slot] = true;
+    g_slots.next[dev] = (slot + 1) % kConstSlots;
     // inside a CUDA-graph capture the guard events cannot be used (they were recorded outside the
     // capture); the captured work is stream-ordered within the graph, which is all it needs
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -93,8 +116,16 @@ struct SlotLease {
     if (!capturing) cudaStreamWaitEvent(st, g_slots.ev[dev][slot], 0);
   }
   ~SlotLease() {
-    if (slot >= 0 && !capturing) cudaEventRecord(g_slots.ev[dev][slot], st);
+    if (slot < 0) return;
+    if (!capturing) cudaEventRecord(g_slots.ev[dev][slot], st);
+    {
+      std::lock_guard<std::mutex> lk(g_slots.m);
+      g_slots.leased[dev][slot] = false;
+    }
+    g_slots.cv.notify_one();
   }
+  SlotLease(const SlotLease &) = delete;
+  SlotLease &operator=(const SlotLease &) = delete;
   bool capturing = false;
 };
 
@@ -343,7 +374,7 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
 // ---- forward rollout (rows a5-a10) -----------------------------------------------------------
 template <typename T>
 static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states, T *feats, int B, int C, int H,
-                       int W, int k, int N, int L, int steps, double dt, void *stream) {
+                       int W, int k, int N, int L, int steps, double dt, void *stream, int rhs_only = 0) {
   if (!u0 || !kernels || !symnet || !states || bad_geom(B, C, H, W, k, N) || L < 0 || steps < 0)
     return PDENET_E_BADARG;
   if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
@@ -359,6 +390,7 @@ static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states
   p.dt = (T)dt;
   p.wrap_y = 1;
   p.u_rows = p.out_rows = H;
+  p.rhs_only = rhs_only;
   for (int t = 0; t < steps; ++t) {
     p.u = t == 0 ? u0 : states + (size_t)(t - 1) * stride;
     p.out = states + (size_t)t * stride;
@@ -636,7 +668,7 @@ template <typename T>
 static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *grad_states, int grad_mode,
                        const T *kernels, const T *symnet, T *grad_u0, T *grad_kernels, T *grad_symnet, void *workspace,
                        size_t ws_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
-                       double dt, void *stream) {
+                       double dt, void *stream, bool identity = true) {
   if (!u0 || !grad_states || !kernels || !symnet || !workspace || bad_geom(B, C, H, W, k, N) || L < 0 ||
       steps < 1 || (steps > 1 && !states) || (grad_mode != PDENET_GRAD_LAST && grad_mode != PDENET_GRAD_ALL))
     return PDENET_E_BADARG;
@@ -698,7 +730,7 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
         q.g = gbuf;
         q.g_rows = H;
         q.wrap_y = 1;
-        q.lam_in = lam_in + boff;
+        q.lam_in = identity ? lam_in + boff : nullptr; // F(u) alone (row a8) has no identity path
         q.li_rows = H;
         q.inject = inject ? inject + boff : nullptr;
         q.inj_rows = H;
@@ -794,9 +826,9 @@ static LinLayout lin_layout(size_t es, int B, int H, int W, int k, int N, int sm
 template <typename T> __global__ void reduce_dcoe_kernel(const T *partial, int B, size_t n, T *out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  T s = T(0);
-  for (int b = 0; b < B; ++b) s += partial[(size_t)b * n + i];
-  out[i] = s;
+  double s = 0.0; // summed in double for either T: the batch can be long
+  for (int b = 0; b < B; ++b) s += (double)partial[(size_t)b * n + i];
+  out[i] = (T)s;
 }
 
 template <typename T>
@@ -1117,7 +1149,12 @@ using namespace pdenet;
 
 extern "C" {
 
-int pdenet_version(void) { return 100; }
+int pdenet_version(void) { return 200; }
+
+#ifndef PDENET_BUILD_ID
+#define PDENET_BUILD_ID "unknown"
+#endif
+const char *pdenet_build_id(void) { return PDENET_BUILD_ID; }
 
 const char *pdenet_error_string(int code) {
   switch (code) {
@@ -1226,6 +1263,31 @@ int pdenet_rollout_fwd_keep_f32(const float *u0, const float *kernels, const flo
                                 void *st) {
   if (!feats) return PDENET_E_BADARG;
   return rollout_fwd<float>(u0, kernels, symnet, states, feats, B, C, H, W, k, N, L, steps, dt, st);
+}
+
+int pdenet_rhs_fwd_f64(const double *u, const double *kernels, const double *symnet, double *out, int B, int C, int H,
+                       int W, int k, int N, int L, void *st) {
+  return rollout_fwd<double>(u, kernels, symnet, out, nullptr, B, C, H, W, k, N, L, 1, 1.0, st, 1);
+}
+int pdenet_rhs_fwd_f32(const float *u, const float *kernels, const float *symnet, float *out, int B, int C, int H,
+                       int W, int k, int N, int L, void *st) {
+  return rollout_fwd<float>(u, kernels, symnet, out, nullptr, B, C, H, W, k, N, L, 1, 1.0, st, 1);
+}
+int pdenet_rhs_bwd_f64(const double *u, const double *grad_out, const double *kernels, const double *symnet,
+                       double *grad_u, double *grad_kernels, double *grad_symnet, void *workspace,
+                       size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                       void *st) {
+  return rollout_bwd<double>(u, nullptr, nullptr, grad_out, PDENET_GRAD_LAST, kernels, symnet, grad_u, grad_kernels,
+                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, 1, 1.0, st,
+                             false);
+}
+int pdenet_rhs_bwd_f32(const float *u, const float *grad_out, const float *kernels, const float *symnet,
+                       float *grad_u, float *grad_kernels, float *grad_symnet, void *workspace,
+                       size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                       void *st) {
+  return rollout_bwd<float>(u, nullptr, nullptr, grad_out, PDENET_GRAD_LAST, kernels, symnet, grad_u, grad_kernels,
+                            grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, 1, 1.0, st,
+                            false);
 }
 
 size_t pdenet_rollout_bwd_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
@@ -1463,12 +1525,13 @@ int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef
 }
 
 int pdenet_profile_enable(int on) {
-  g_prof.on = on != 0;
+  g_prof.on.store(on != 0);
   return PDENET_OK;
 }
 int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind) {
   double ms[PDENET_PROF_KINDS] = {0, 0, 0, 0, 0};
   int rc = PDENET_OK;
+  std::lock_guard<std::mutex> lk(g_prof.m);
   for (auto &r : g_prof.recs) {
     float t = 0.f;
     if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess)
@@ -1480,8 +1543,8 @@ int pdenet_profile_read(double *ms_by_kind, long long *launches_by_kind) {
   g_prof.recs.clear();
   for (int i = 0; i < PDENET_PROF_KINDS; ++i) {
     if (ms_by_kind) ms_by_kind[i] = ms[i];
-    if (launches_by_kind) launches_by_kind[i] = g_prof.launches[i];
-    g_prof.launches[i] = 0;
+    const long long n = g_prof.launches[i].exchange(0);
+    if (launches_by_kind) launches_by_kind[i] = n;
   }
   return rc;
 }

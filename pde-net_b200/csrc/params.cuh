@@ -38,6 +38,7 @@ template <typename T> struct StepParams {
   T *feats;
   double *sym_partial; // [gridDim.x][C*Psym], accumulated across launches
   int skip_sym_grad;   // 1: ghost-row launch of a slab -- emit g only, contribute no parameter gradient
+  int rhs_only;        // MODE_FWD: 1 = write F(u) = SymNet(FD2d(u)) itself instead of the Euler update (row a8)
   T *dcoe_partial;     // linear modes: [B][N-1][H][W], accumulated across launches
   int B, H, W, L, Psym;
   T dt;

@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 #pragma unroll
           for (int j = 0; j < P; ++j)
             if (valid[j]) {
-              const T v = fma_(p.dt, fout[j], uc[j * PITCH]);
+              const T v = p.rhs_only ? fout[j] : fma_(p.dt, fout[j], uc[j * PITCH]);
               op[(size_t)j * W] = v;
               if (p.mirror_rows) { // fused halo exchange: peer stores over NVLink
                 const int y = y0 + j;
@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
         // row a12: u+ = D0*u + dt * sum_n coe_n (D_n*u); filter 0 is D0, C == 1.  Loads of the
         // coefficient fields are issued for the whole strip before use (running pointers).
         const size_t plane = (size_t)H * W;
-        const T *cp = p.symnet + (size_t)y0 * W + x;
+        const int xc = x < W ? x : 0; // lanes right of the grid read column 0 (discarded): stays in bounds
+        const T *cp = p.symnet + (size_t)y0 * W + xc;
         T acc[P];
 #pragma unroll
         for (int j = 0; j < P; ++j) acc[j] = T(0);
@@ -748,8 +749,9 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 #pragma unroll
         for (int j = 0; j < P; ++j)
           if (valid[j]) gp[(size_t)j * W] = lam[j];
-        const T *cp = p.symnet + (size_t)y0 * W + x;
-        T *dc = p.dcoe_partial + (size_t)b * (N - 1) * plane + (size_t)y0 * W + x;
+        const int xc = x < W ? x : 0; // invalid lanes load from column 0 (in bounds) and never store
+        const T *cp = p.symnet + (size_t)y0 * W + xc;
+        T *dc = p.dcoe_partial + (size_t)b * (N - 1) * plane + (size_t)y0 * W + xc;
         // batches of 4 filters: all loads of a batch are issued before its stores (the compiler
         // cannot move loads across the stores itself -- the pointers may alias)
         constexpr int NB = 4;

@@ -62,7 +62,7 @@ def training_loss(model, u0: torch.Tensor, observed: torch.Tensor, block_weights
     (weights ``block_weights``, default 1 each) and add the two sparsity terms scaled by the number
     of blocks.  Returns the scalar loss with the autograd graph attached."""
     blocks = observed.shape[0]
-    states = model.multistep(u0, blocks * model.dt, all_states=True)
+    states = model.multistep(u0, blocks, all_states=True)
     loss = ops.mse_loss(states, observed, block_weights)
     if sparsity:
         loss = loss + (blocks * sparsity) * symnet_sparsity(model, symnet_threshold)
@@ -80,26 +80,30 @@ class GraphedTrainingLoss:
     updates them in place (``optim.FlatParams.set_flat``) needs no re-capture; ``u0`` / ``observed``
     are copied into static buffers (``set_data`` swaps in a new batch of the same shape).
     ``__call__()`` returns ``(loss, flat_grad)``: device tensors that the next replay overwrites;
-    ``flat_grad`` follows the order of ``model.parameters()`` with ``requires_grad`` (the order of
-    ``FlatParams``), pinned moment entries already zero."""
+    ``flat_grad`` IS the model's flat gradient buffer (``optim.FlatParams.gflat``, attached on
+    construction if the model has none yet; order of ``model.parameters()`` with ``requires_grad``),
+    pinned moment entries already zero."""
 
     def __init__(self, model, u0: torch.Tensor, observed: torch.Tensor, block_weights: Optional[Sequence[float]] = None,
                  sparsity: float = 0.0, momentsparsity: float = 0.0, symnet_threshold: float = 1e-3,
                  moment_threshold: float = 1e-2, warmup: int = 3):
         if not u0.is_cuda:
             raise RuntimeError("GraphedTrainingLoss needs CUDA tensors (there is no CPU path)")
+        from .optim import FlatParams
         self.model = model
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        # parameters / gradients live in persistent flat buffers (optim.FlatParams): the captured graph
+        # zeroes ONE buffer, accumulates into it and hands out a view of it -- no cat, no re-allocation
+        self.flat = model.__dict__.get("_flat") or FlatParams(model)
+        self.params = self.flat.params
         self.u0, self.observed = u0.detach().clone(), observed.detach().clone()
         kw = dict(block_weights=block_weights, sparsity=sparsity, momentsparsity=momentsparsity,
                   symnet_threshold=symnet_threshold, moment_threshold=moment_threshold)
 
         def evaluate():
+            self.flat.zero_grad()
             loss = training_loss(model, self.u0, self.observed, **kw)
-            grads = torch.autograd.grad(loss, self.params, allow_unused=True)
-            flat = torch.cat([(g if g is not None else torch.zeros_like(p)).reshape(-1)
-                              for g, p in zip(grads, self.params)])
-            return loss.detach(), flat
+            loss.backward()
+            return loss.detach(), self.flat.grad_flat()
 
         cur = torch.cuda.current_stream(u0.device)
         side = torch.cuda.Stream(u0.device)

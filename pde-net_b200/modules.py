@@ -26,6 +26,26 @@ def _pair(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
+def _bank_kernels(model, fds) -> torch.Tensor:
+    """Scaled kernels [len(fds), k, k] of a list of FD2d filters: one fused m2k call.  With a
+    ``FlatParams`` attached (``optim.FlatParams(model)``) the moments are read as ONE zero-copy view of
+    the flat parameter buffer and their gradient is accumulated straight into the flat gradient
+    buffer; otherwise they are stacked.  The pinned-entry mask is static and cached per device."""
+    fp = getattr(model, "_flat", None)
+    k = fds[0].kernel_size
+    if fp is not None:
+        moments = fp.group([fd.moment for fd in fds], (len(fds), k, k))
+    else:
+        moments = torch.stack([fd.moment for fd in fds])
+    cache = model.__dict__.setdefault("_bank_cache", {})
+    key = (tuple(id(fd) for fd in fds), moments.device)
+    if key not in cache:
+        cache[key] = (torch.stack([fd._pinned for fd in fds]).to(moments.device, torch.uint8).contiguous(),
+                      [fd.scale for fd in fds])
+    mask, scales = cache[key]
+    return ops.m2k(moments, scales, mask)
+
+
 class M2K(nn.Module):
     """Moment matrix -> convolution kernel (row a2).  ``shape`` is the kernel shape (k, k)."""
 
@@ -190,33 +210,52 @@ class POLYPDE2D(nn.Module):
             fd.grad_proj()
 
     # ---- pieces of the step
+    def _attach_flat(self, fp) -> None:
+        """Called by ``optim.FlatParams(model)``: parameters are now views of one flat buffer."""
+        self.__dict__["_flat"] = fp
+
     def scaled_kernels(self) -> torch.Tensor:
-        fds = self.fds
-        moments = torch.stack([fd.moment for fd in fds])
-        mask = torch.stack([fd._pinned for fd in fds])
-        return ops.m2k(moments, [fd.scale for fd in fds], mask)
+        return _bank_kernels(self, self.fds)
 
     def symnet_flat(self) -> torch.Tensor:
+        """[C, Psym] in the C-ABI layout.  With a ``FlatParams`` attached this is a zero-copy view of
+        the flat parameter buffer (the nn.Linear parameters of ``poly0..`` are laid out in exactly
+        that order) whose gradient goes straight into the flat gradient buffer."""
+        fp = self.__dict__.get("_flat")
+        if fp is not None:
+            ps = [q for pl in self.polys for q in pl.parameters()]
+            return fp.group(ps, (self.channel_num, sum(q.numel() for q in ps) // self.channel_num))
         return torch.stack([pl.flat_params() for pl in self.polys])
 
     def UInputs(self, u: torch.Tensor) -> torch.Tensor:
-        """[B,C,H,W] -> channels-last derivative features [B,H,W,C*N]."""
+        """[B,C,H,W] -> channels-last derivative features [B,H,W,C*N] (feature index c*N + n)."""
         return ops.fd2d(u, self.scaled_kernels()).permute(0, 2, 3, 1)
 
     def RightHandItems(self, u: torch.Tensor) -> torch.Tensor:
-        """F(u) [B,C,H,W] = (one fused step - u) / dt."""
-        return (self.predict(u) - u) / self.dt
+        """F(u) [B,C,H,W]: the fused step kernel writing the SymNet output itself (no Euler update,
+        no differencing of states)."""
+        return ops.rhs(u, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.batch_chunk)
 
     def predict(self, u: torch.Tensor) -> torch.Tensor:
-        return self.multistep(u, self.dt)
+        """One forward-Euler step ``u + dt*F(u)``."""
+        return self.multistep(u, 1)
 
-    def multistep(self, inputs: torch.Tensor, T: float, all_states: bool = False) -> torch.Tensor:
-        steps = max(1, int(round(T / self.dt)))
-        return ops.rollout(inputs, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.dt, steps,
-                           last_only=not all_states, batch_chunk=self.batch_chunk, keep_features=self.keep_features)
+    def multistep(self, inputs: torch.Tensor, stepnum: int, all_states: bool = False) -> torch.Tensor:
+        """``stepnum`` forward-Euler steps (a step COUNT, as upstream's ``multistep(inputs, stepnum)``;
+        ``forward(init, T)`` is the entry that takes a time).  One fused CUDA rollout."""
+        if int(stepnum) != stepnum or stepnum < 1:
+            raise ValueError("stepnum must be a positive integer, got %r" % (stepnum,))
+        return ops.rollout(inputs, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.dt,
+                           int(stepnum), last_only=not all_states, batch_chunk=self.batch_chunk,
+                           keep_features=self.keep_features)
 
-    def forward(self, init: torch.Tensor, T: float) -> torch.Tensor:
-        return self.multistep(init, T)
+    def forward(self, init: torch.Tensor, T: float, all_states: bool = False) -> torch.Tensor:
+        """State after time ``T``; ``T`` must be a whole number of steps of ``dt`` (as upstream, which
+        refuses anything else instead of rounding silently)."""
+        stepnum = round(T / self.dt)
+        if stepnum < 1 or abs(stepnum - T / self.dt) > 1e-5:
+            raise NotImplementedError("T=%r is not a positive whole multiple of dt=%r" % (T, self.dt))
+        return self.multistep(init, stepnum, all_states=all_states)
 
 
 class LagrangeInterpFixInputs2d(nn.Module):
@@ -316,11 +355,11 @@ class VariantCoeLinear2d(nn.Module):
         for fd in [self.id] + self.fds:
             fd.grad_proj()
 
+    def _attach_flat(self, fp) -> None:
+        self.__dict__["_flat"] = fp
+
     def scaled_kernels(self):
-        fds = [self.id] + self.fds
-        moments = torch.stack([fd.moment for fd in fds])
-        mask = torch.stack([fd._pinned for fd in fds])
-        return ops.m2k(moments, [fd.scale for fd in fds], mask)
+        return _bank_kernels(self, [self.id] + self.fds)
 
     def forward(self, init: torch.Tensor, stepnum: int, all_states: bool = False) -> torch.Tensor:
         ks = self.scaled_kernels()
@@ -381,6 +420,7 @@ class SingleNonLinear2d(nn.Module):
     diff_x_proj = VariantCoeLinear2d.diff_x_proj
     diff_grad_proj = VariantCoeLinear2d.diff_grad_proj
     scaled_kernels = VariantCoeLinear2d.scaled_kernels
+    _attach_flat = VariantCoeLinear2d._attach_flat
 
     def diff_params(self):
         return (fd.moment for fd in [self.id] + self.fds)

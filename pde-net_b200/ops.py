@@ -244,6 +244,51 @@ def rollout(u0: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: in
                           keep_features)
 
 
+# ------------------------------------------------------------------------------ row a8
+class _Rhs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, kernels, symnet, L, batch_chunk):
+        u = _req(u, "u")
+        kernels = _req(kernels, "kernels", u.dtype)
+        symnet = _req(symnet, "symnet", u.dtype)
+        B, Cc, H, W = u.shape
+        N, k, _ = kernels.shape
+        if tuple(symnet.shape) != (Cc, symnet_param_count(Cc * N, L)):
+            raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
+                             % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
+        out = torch.empty_like(u)
+        _lib.check(_lib.fn("pdenet_rhs_fwd", u.dtype)(_ptr(u), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, H, W, k,
+                                                      N, L, _stream()), "pdenet_rhs_fwd")
+        ctx.save_for_backward(u, kernels, symnet)
+        ctx.cfg = (L, batch_chunk)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        u, kernels, symnet = ctx.saved_tensors
+        L, batch_chunk = ctx.cfg
+        B, Cc, H, W = u.shape
+        N, k, _ = kernels.shape
+        grad = _req(grad, "grad_out", u.dtype)
+        nbytes = _lib.lib().pdenet_rollout_bwd_workspace_bytes(u.element_size(), B, Cc, H, W, k, N, L, batch_chunk)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u.device)
+        need_u, need_k, need_s = ctx.needs_input_grad[:3]
+        gu = torch.empty_like(u) if need_u else None
+        gk = torch.empty_like(kernels) if need_k else None
+        gs = torch.empty_like(symnet) if need_s else None
+        _lib.check(_lib.fn("pdenet_rhs_bwd", u.dtype)(
+            _ptr(u), _ptr(grad), _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs), _ptr(ws), nbytes,
+            batch_chunk, B, Cc, H, W, k, N, L, _stream()), "pdenet_rhs_bwd")
+        return gu, gk, gs, None, None
+
+
+def rhs(u: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, batch_chunk: int = 0) -> torch.Tensor:
+    """The right-hand side ``F(u) = SymNet(FD2d(u))`` [B,C,H,W] itself (row a8, upstream
+    ``POLYPDE2D.RightHandItems``): the fused step kernel without the Euler update, differentiable
+    w.r.t. ``u``, the scaled ``kernels`` and the flat ``symnet``."""
+    return _Rhs.apply(u, kernels, symnet, int(L), int(batch_chunk))
+
+
 # ------------------------------------------------------------------------------ row a12
 class _LinearRollout(torch.autograd.Function):
     @staticmethod

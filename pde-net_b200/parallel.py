@@ -48,8 +48,12 @@ def flat_allreduce(tensors: Sequence[torch.Tensor], group=None, extra: Optional[
     return flat[n] if extra is not None else None
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, loss: Optional[torch.Tensor] = None):
-    """Data-parallel gradient exchange: one all-reduce for every ``.grad`` (and the loss)."""
+def allreduce_gradients(params, group=None, loss: Optional[torch.Tensor] = None):
+    """Data-parallel gradient exchange: one all-reduce for every ``.grad`` (and the loss).
+    ``params``: an ``optim.FlatParams`` (the gradients already live in one flat buffer: reduced in
+    place, nothing packed or unpacked) or any iterable of parameters (packed into a flat buffer)."""
+    if hasattr(params, "allreduce"):
+        return params.allreduce(loss=loss, group=group)
     grads = [p.grad for p in params if p.grad is not None]
     return flat_allreduce(grads, group=group, extra=loss)
 

@@ -101,14 +101,62 @@ def test_flat_params_view(built):
         assert torch.equal(blk[~fd._pinned], x[o:o + 25].reshape(5, 5)[~fd._pinned])
         o += 25
     assert torch.equal(got[o:], x[o:])
+    # parameters and gradients are views of the two persistent flat buffers
+    fp.check()
+    es = fp.flat.element_size()
     for p in m.parameters():
-        p.grad = torch.ones_like(p)
+        assert p.data_ptr() == fp.flat.data_ptr() + fp.offsets[id(p)] * es
+        p.grad.fill_(1)                  # in place: the .grad views stay attached
     g = fp.grad_flat()
+    assert g.data_ptr() == fp.gflat.data_ptr()
     o = 0
     for fd in m.fds:
         assert (g[o:o + 25].reshape(5, 5)[fd._pinned] == 0).all()
         o += 25
     assert (g[o:] == 1).all()
+    fp.zero_grad()
+    assert all((p.grad == 0).all() for p in m.parameters())
+    fp.check()
+    # the zero-copy groups the fused rollout consumes: moments [N,k,k] and SymNet [C,Psym]
+    sym = m.symnet_flat()
+    assert sym.data_ptr() == next(m.poly0.parameters()).data_ptr() and sym.shape == (2, 69)
+    assert torch.equal(sym.detach(), torch.stack([pl.flat_params() for pl in m.polys]).detach())
+    (sym * 2.0).sum().backward()         # one accumulate into the flat gradient buffer
+    assert (fp.gflat[6 * 25:] == 2).all() and (fp.gflat[:6 * 25] == 0).all()
+    # re-allocating a parameter behind FlatParams' back is detected
+    m.fd00.moment.grad = None
+    with pytest.raises(RuntimeError):
+        fp.check()
+
+
+def test_numpy_function_interface_lbfgs(built):
+    """NumpyFunctionInterface (upstream aTEAM.optim names): flat_param / f / fprime drive SciPy's
+    L-BFGS on a small quadratic; param-group x_proj / grad_proj hooks are applied."""
+    import numpy as np
+    from scipy.optimize import fmin_l_bfgs_b
+    a = torch.nn.Parameter(torch.zeros(3, dtype=torch.float64))
+    b = torch.nn.Parameter(torch.ones(2, 2, dtype=torch.float64))
+    ta, tb = torch.tensor([1.0, -2.0, 3.0], dtype=torch.float64), torch.full((2, 2), 0.5, dtype=torch.float64)
+
+    def pin_first(params):               # keep b[0,0] at 1 (an x_proj), and never move it (grad_proj)
+        with torch.no_grad():
+            params[0][0, 0] = 1.0
+
+    def zero_first(params):
+        params[0].grad[0, 0] = 0.0
+
+    nfi = built.NumpyFunctionInterface(
+        [dict(params=[a]), dict(params=[b], x_proj=pin_first, grad_proj=zero_first)],
+        forward=lambda: ((a - ta) ** 2).sum() + ((b - tb) ** 2).sum())
+    assert nfi.numel() == 7 and nfi.numel == 7 and nfi.flat_param.shape == (7,)
+    x, f, d = fmin_l_bfgs_b(nfi.f, nfi.flat_param, nfi.fprime, m=10, factr=1e1, pgtol=1e-12)
+    assert d["warnflag"] == 0
+    nfi.flat_param = x
+    assert torch.allclose(a.detach(), ta, atol=1e-7)
+    assert b.detach()[0, 0] == 1.0 and torch.allclose(b.detach().reshape(-1)[1:], tb.reshape(-1)[1:], atol=1e-7)
+    assert abs(f - 0.25) < 1e-10         # the pinned entry's misfit (1 - 0.5)^2 is all that is left
+    g = nfi.fprime(x)
+    assert g.dtype == np.float64 and g[3] == 0.0
 
 
 def test_lagrange_interp_fields(built):

@@ -90,6 +90,16 @@ def _worker(rank, world, port, q):
         loss = out.square().sum() / u0[0].numel() / u0.shape[0]
         loss.backward()
         total = PP.flat_allreduce([Kc.grad, sc.grad], extra=loss.detach())
+        # ---- 8f-4: gradients that already live in one flat buffer are reduced in place (no packing)
+        lin = torch.nn.Linear(3, 2).double()
+        fp = pdenet_b200.FlatParams(lin)
+        fp.gflat.copy_(torch.arange(fp.numel, dtype=torch.float64) * (rank + 1))
+        ptr = fp.gflat.data_ptr()
+        red = PP.allreduce_gradients(fp, loss=torch.tensor(float(rank + 1), dtype=torch.float64))
+        tri = world * (world + 1) / 2
+        assert fp.gflat.data_ptr() == ptr and float(red) == tri
+        assert torch.equal(lin.weight.grad.reshape(-1), torch.arange(6, dtype=torch.float64) * tri)
+        assert torch.equal(lin.bias.grad, torch.arange(6, 8, dtype=torch.float64) * tri)
         # ---- DIST-1: slab decomposition with ring halo exchange
         slab = PP.SlabDecomposition(u0.shape[2], 2, rank, world)
         mine = u0[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
