@@ -43,7 +43,7 @@ __all__ = [
     "order_list", "moment_axis_matrix", "m2k", "k2m", "initial_moments", "pinned_mask",
     "filter_scales", "scaled_kernels", "periodic_pad", "fd2d_apply", "symnet_param_count",
     "symnet_unpack", "symnet_apply", "right_hand_items", "step", "rollout",
-    "linear_step", "linear_rollout",
+    "linear_step", "linear_rollout", "burgers_symnet", "stable_burgers_model",
 ]
 
 
@@ -201,6 +201,51 @@ def rollout(u0, Ks, symnet, L, dt, steps: int):
         u = step(u, Ks, symnet, L, dt)
         states.append(u)
     return states
+
+
+# ----------------------------------------------------------------------------- synthetic models
+def burgers_symnet(nu: float, N: int = 6, C: int = 2, L: int = 2) -> torch.Tensor:
+    """Hand-set SymNet weights (KAT-4): channel c -> ``-u w_x - v w_y + nu (w_xx + w_yy)``, w = u or v.
+
+    Feature index f = c*N + n with orders (0,0),(0,1),(1,0),(0,2),(1,1),(2,0);
+    (0,1) is d/dx (axis W), (1,0) is d/dy (axis H).  Two product units suffice (L = 2).
+    """
+    assert N >= 6 and C == 2 and L == 2
+    m = C * N
+    sym = torch.zeros(C, symnet_param_count(m, L), dtype=torch.float64)
+    iu, iv = 0, N
+    for c in range(C):
+        base = c * N
+        W0 = torch.zeros(2, m, dtype=torch.float64)
+        W0[0, iu] = 1; W0[1, base + 1] = 1        # p0 = u,  q0 = w_x
+        W1 = torch.zeros(2, m + 1, dtype=torch.float64)
+        W1[0, iv] = 1; W1[1, base + 2] = 1        # p1 = v,  q1 = w_y
+        wf = torch.zeros(m + L, dtype=torch.float64)
+        wf[m] = -1; wf[m + 1] = -1
+        wf[base + 3] = nu; wf[base + 5] = nu
+        z2 = torch.zeros(2, dtype=torch.float64)
+        sym[c] = torch.cat([W0.flatten(), z2, W1.flatten(), z2, wf, torch.zeros(1, dtype=torch.float64)])
+    return sym
+
+
+def stable_burgers_model(k: int, dx: float, nu: float = 0.05, noise: float = 1e-2, moment_noise: float = 1e-3,
+                         seed: int = 0):
+    """Synthetic model for parity / benchmark runs on fine grids: viscous Burgers (KAT-4 weights) with
+    ``noise * N(0,1)`` added to EVERY SymNet entry and ``moment_noise * N(0,1)`` to every non-pinned moment
+    entry (1e-2 there puts an anti-diffusive grid-scale response of ~0.85 per step into the 1/dx^2-scaled
+    filters at 128^2, dt = 1e-3, which single precision does not survive for 15 steps), so that all
+    parameter gradients are non-trivial while forward Euler stays stable for ``dt <= 2.5 dx^2`` at
+    ``nu = 0.05`` (diffusion number ``nu dt ||K_xx||_1 = 0.05 * 2.5 * 6.04 = 0.75 < 2``).  (A fully random SymNet -- N(0, 0.1^2) on the
+    second-derivative inputs -- is anti-diffusive half of the time and blows up within a few steps on
+    128^2 and finer grids.)  Returns ``(orders, moments [6,k,k], scales [6], symnet [2,69])``, all fp64."""
+    orders = order_list(2)
+    g = torch.Generator().manual_seed(seed)
+    M = initial_moments(k, orders)
+    for n, o in enumerate(orders):
+        free = ~pinned_mask(k, o, "moment")
+        M[n] += moment_noise * torch.randn(k, k, generator=g, dtype=torch.float64) * free
+    sym = burgers_symnet(nu) + noise * torch.randn(2, symnet_param_count(12, 2), generator=g, dtype=torch.float64)
+    return orders, M, filter_scales(orders, dx), sym
 
 
 # ----------------------------------------------------------------------------- a12

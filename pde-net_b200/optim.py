@@ -137,6 +137,12 @@ class FlatParams:
             self.grad_proj()
         return self.gflat
 
+    @property
+    def grad_and_loss(self) -> torch.Tensor:
+        """The whole gradient buffer ``[numel + 1]``: flat gradient, then the loss slot that
+        :meth:`allreduce` fills -- one D2H copy brings back everything an optimiser step needs."""
+        return self._gbuf
+
     def zero_grad(self) -> None:
         self._gbuf.zero_()                          # one memset; the .grad views stay attached
 

@@ -183,3 +183,18 @@ def test_lagrange_interp_fields(built):
     assert li.interp_coe.grad is not None and li.interp_coe.grad.abs().sum() > 0
     m = built.VariantCoeLinear2d(5, 2, 0.1, 1e-3, (H, W), interp_degree=2, interp_mesh_size=mesh)
     assert m.coefficient_fields().shape == (5, H, W) and len(list(m.coe_params())) == 1
+
+
+def test_bench_model_equals_oracle_model(built):
+    """bench.py builds its synthetic Burgers model without importing the oracle (product arm); it is the
+    same model, number for number, as oracle.stable_burgers_model (the parity leg compares the two sides)."""
+    import math
+
+    import bench
+    from oracle import pdenet_oracle as O
+    dx = 2 * math.pi / 1024
+    orders, M, scales, sym = bench.model_params(7, 2, 2, 2, dx)
+    o2, M2, s2, sym2 = O.stable_burgers_model(7, dx)
+    assert orders == o2 and torch.equal(M, M2) and torch.equal(sym, sym2)
+    assert torch.equal(torch.tensor(scales, dtype=torch.float64), s2)
+    assert bench.step_dt(dx) == 2.5 * dx * dx

@@ -77,27 +77,7 @@ def test_kat3_truncation_error(k, tol):
 
 
 # KAT-4 ------------------------------------------------------------------
-def burgers_symnet(nu, N=6, C=2, L=2):
-    """Hand-set SymNet weights: channel 0 -> -u u_x - v u_y + nu lap u, channel 1 likewise.
-
-    Feature index f = c*N + n with orders (0,0),(0,1),(1,0),(0,2),(1,1),(2,0);
-    (0,1) is d/dx (axis W), (1,0) is d/dy (axis H).
-    """
-    m = C * N
-    P = O.symnet_param_count(m, L)
-    sym = torch.zeros(C, P)
-    iu, iv = 0, N
-    for c in range(C):
-        base = c * N
-        W0 = torch.zeros(2, m); b0 = torch.zeros(2)
-        W0[0, iu] = 1; W0[1, base + 1] = 1        # p0 = u,  q0 = w_x
-        W1 = torch.zeros(2, m + 1); b1 = torch.zeros(2)
-        W1[0, iv] = 1; W1[1, base + 2] = 1        # p1 = v,  q1 = w_y
-        wf = torch.zeros(m + L)
-        wf[m] = -1; wf[m + 1] = -1
-        wf[base + 3] = nu; wf[base + 5] = nu
-        sym[c] = torch.cat([W0.flatten(), b0, W1.flatten(), b1, wf, torch.zeros(1)])
-    return sym
+burgers_symnet = O.burgers_symnet   # the hand-wired weights live in the oracle (also used by bench.py's parity leg)
 
 
 def test_kat4_burgers_step_matches_independent_numpy():

@@ -108,7 +108,9 @@ def _worker(rank, world, port, q):
         wloc = _weights(u0)[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
         fin2, gu0, sgk, sgs = slab.rollout_fwd_bwd(mine, Ks, sym, L, dt, steps, lambda f: wloc,
                                                    step_fn=_oracle_slab_step, bwd_factory=_OracleSlabBackward)
-        q.put((rank, Kc.grad, sc.grad, float(total), fin, fin2, gu0, sgk, sgs))
+        # by value (numpy), not as shared-memory tensors: the worker may exit before the parent reads
+        q.put(tuple(t.detach().numpy() if torch.is_tensor(t) else t
+                    for t in (rank, Kc.grad, sc.grad, float(total), fin, fin2, gu0, sgk, sgs)))
     finally:
         dist.destroy_process_group()
 
@@ -121,7 +123,8 @@ def test_dp_and_slab_world2():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    res = sorted([tuple(torch.from_numpy(t) if hasattr(t, "dtype") and hasattr(t, "shape") and getattr(t, "ndim", 0) > 0
+                        else t for t in q.get(timeout=240)) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 import pdenet_b200 as P
 from pdenet_b200 import parallel as PP
-from bench import model_params, synth_fields
+from bench import model_params, step_dt, synth_fields
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
     H = W = a.size
     k, C, L = 7, 2, 2
     dx = 2 * math.pi / W
-    dt = 0.25 * dx * dx
+    dt = step_dt(dx)
     orders, M, scales, sym = model_params(k, 2, C, L, dx)
     Ks = P.m2k(M.to(dev, dtype), scales)
     sym = sym.to(dev, dtype)
