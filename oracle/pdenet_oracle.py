@@ -234,8 +234,8 @@ def stable_burgers_model(k: int, dx: float, nu: float = 0.05, noise: float = 1e-
     ``noise * N(0,1)`` added to EVERY SymNet entry and ``moment_noise * N(0,1)`` to every non-pinned moment
     entry (1e-2 there puts an anti-diffusive grid-scale response of ~0.85 per step into the 1/dx^2-scaled
     filters at 128^2, dt = 1e-3, which single precision does not survive for 15 steps), so that all
-    parameter gradients are non-trivial while forward Euler stays stable for ``dt <= 2.5 dx^2`` at
-    ``nu = 0.05`` (diffusion number ``nu dt ||K_xx||_1 = 0.05 * 2.5 * 6.04 = 0.75 < 2``).  (A fully random SymNet -- N(0, 0.1^2) on the
+    parameter gradients are non-trivial while forward Euler stays stable with margin at ``dt = dx^2``,
+    ``nu = 0.05`` (diffusion number ``nu dt ||K_xx||_1 = 0.05 * 6.04 = 0.3`` per direction).  (A fully random SymNet -- N(0, 0.1^2) on the
     second-derivative inputs -- is anti-diffusive half of the time and blows up within a few steps on
     128^2 and finer grids.)  Returns ``(orders, moments [6,k,k], scales [6], symnet [2,69])``, all fp64."""
     orders = order_list(2)

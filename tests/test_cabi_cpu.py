@@ -197,4 +197,4 @@ def test_bench_model_equals_oracle_model(built):
     o2, M2, s2, sym2 = O.stable_burgers_model(7, dx)
     assert orders == o2 and torch.equal(M, M2) and torch.equal(sym, sym2)
     assert torch.equal(torch.tensor(scales, dtype=torch.float64), s2)
-    assert bench.step_dt(dx) == 2.5 * dx * dx
+    assert bench.step_dt(dx) == dx * dx
