@@ -147,6 +147,44 @@ PDENET_API int pdenet_rollout_bwd_f32(const float *u0, const float *states, cons
                            float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
                            int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
 
+/* ---- row f-1: pseudo-upwind scheme (upstream polypde.py::POLYPDE2D(scheme='upwind'); restated from
+ * the description in arXiv 1812.04426 -- the upstream source is not in the mount, so UNPINNED) ------
+ * Same arguments and layouts as the central entries above (`kernels` is still the N-filter bank, in bank
+ * order: index 1 = order (0,1) along W, index 2 = order (1,0) along H).  Per output channel co and grid
+ * point, each first-order input (c, dir) of SymNet_co is taken from the filter as given when the local
+ * velocity a = d SymNet_co / d feature (evaluated at the central features) is >= 0, and from its flipped
+ * twin  K-[a,b] = -K[a,k-1-b]  (dir W)  /  -K[k-1-a,b]  (dir H)  when a < 0; the selection is treated
+ * as constant by the reverse pass.  Twins are evaluated from the already staged tile; the reverse
+ * pass returns the gradient folded back onto the N filters.  Supported: N in {3, 6}, C in {1, 2}. */
+PDENET_API int pdenet_upwind_supported(int elem_size, int k, int N, int C, int L);
+PDENET_API int pdenet_rollout_fwd_upwind_f64(const double *u0, const double *kernels, const double *symnet, double *states,
+                                  int B, int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API int pdenet_rollout_fwd_upwind_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API size_t pdenet_rollout_bwd_upwind_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
+                                                 int batch_chunk);
+PDENET_API int pdenet_rollout_bwd_upwind_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                                  const double *kernels, const double *symnet, double *grad_u0, double *grad_kernels,
+                                  double *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+PDENET_API int pdenet_rollout_bwd_upwind_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                                  const float *kernels, const float *symnet, float *grad_u0, float *grad_kernels,
+                                  float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *stream);
+/* F(u) itself under the upwind scheme (row a8 with scheme='upwind'); workspace as pdenet_rollout_bwd_upwind_*. */
+PDENET_API int pdenet_rhs_upwind_fwd_f64(const double *u, const double *kernels, const double *symnet, double *out, int B,
+                              int C, int H, int W, int k, int N, int L, void *stream);
+PDENET_API int pdenet_rhs_upwind_fwd_f32(const float *u, const float *kernels, const float *symnet, float *out, int B, int C,
+                              int H, int W, int k, int N, int L, void *stream);
+PDENET_API int pdenet_rhs_upwind_bwd_f64(const double *u, const double *grad_out, const double *kernels, const double *symnet,
+                              double *grad_u, double *grad_kernels, double *grad_symnet, void *workspace,
+                              size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                              void *stream);
+PDENET_API int pdenet_rhs_upwind_bwd_f32(const float *u, const float *grad_out, const float *kernels, const float *symnet,
+                              float *grad_u, float *grad_kernels, float *grad_symnet, void *workspace,
+                              size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                              void *stream);
+
 /* Feature-keeping variant of the rollout (same results, bit for bit; trades HBM for FP64 work).
  * pdenet_rollout_fwd_keep_* additionally stores the C*N derivative features of every step's
  * INPUT state: feats[t] = FD bank applied to u_t, t = 0..steps-1, layout [steps][B][C*N][H][W]

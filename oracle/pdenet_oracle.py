@@ -44,6 +44,7 @@ __all__ = [
     "filter_scales", "scaled_kernels", "periodic_pad", "fd2d_apply", "symnet_param_count",
     "symnet_unpack", "symnet_apply", "right_hand_items", "step", "rollout",
     "linear_step", "linear_rollout", "burgers_symnet", "stable_burgers_model",
+    "upwind_twins", "upwind_right_hand_items", "upwind_step", "upwind_rollout",
 ]
 
 
@@ -199,6 +200,65 @@ def rollout(u0, Ks, symnet, L, dt, steps: int):
     states, u = [], u0
     for _ in range(steps):
         u = step(u, Ks, symnet, L, dt)
+        states.append(u)
+    return states
+
+
+# ----------------------------------------------------------------------------- f-1
+def upwind_twins(Ks: torch.Tensor) -> torch.Tensor:
+    """Row f-1.  The flipped twins of the two first-order filters of a bank in bank order (index 1 =
+    order (0,1), derivative along W; index 2 = order (1,0), along H): mirror along the derivative axis
+    and negate, ``K1-[a,b] = -K1[a,k-1-b]``, ``K2-[a,b] = -K2[k-1-a,b]`` -- the same derivative with
+    the opposite one-sided bias (a centred filter is its own twin).  Returns ``[2, k, k]``."""
+    return torch.stack([-torch.flip(Ks[1], dims=(1,)), -torch.flip(Ks[2], dims=(0,))])
+
+
+def upwind_right_hand_items(u: torch.Tensor, Ks: torch.Tensor, symnet: torch.Tensor, L: int) -> torch.Tensor:
+    """Row f-1: ``RightHandItems`` under ``scheme='upwind'`` (pseudo-upwind).
+
+    [PAPER, UNPINNED]  Restated from the description of the pseudo-upwind scheme in PDE-Net 2.0
+    (arXiv 1812.04426, README.md:6): the first-order derivative inputs of the SymNet are taken from a
+    one-sided ("upwind") version of their filter, the side being chosen point by point from the sign of
+    the local convection velocity, which the network itself supplies as the derivative of its output
+    with respect to that input.  The upstream implementation (branch ``PDE-Net-2.0``, ``polypde.py``)
+    is not in the mount; the conventions below are this repository's explicit choices:
+
+    * for output channel ``co`` and every first-order input ``f = c*N + n`` (``n = 1``: d/dx along W,
+      ``n = 2``: d/dy along H) the velocity is ``a = d SymNet_co / d x_f`` evaluated at the CENTRAL
+      features (all filters as given);
+    * ``a >= 0``: the input stays ``K_n * u_c``;  ``a < 0``: it becomes ``K_n- * u_c`` with the flipped
+      twin of :func:`upwind_twins`;
+    * every SymNet sees its own selection; the selection is piecewise constant and is treated as a
+      constant by the reverse pass (``detach``).
+    """
+    B, C, H, W = u.shape
+    N = Ks.shape[0]
+    d = fd2d_apply(u, Ks).permute(0, 2, 3, 1)                       # [B,H,W,C*N] central features
+    dt = fd2d_apply(u, upwind_twins(Ks)).permute(0, 2, 3, 1)        # [B,H,W,C*2] twins, index 2c + dir
+    out = []
+    for co in range(C):
+        with torch.enable_grad():
+            x = d.detach().requires_grad_(True)
+            a, = torch.autograd.grad(symnet_apply(x, symnet[co].detach(), L).sum(), x)
+        cols = []
+        for f in range(C * N):
+            c, n = divmod(f, N)
+            if n in (1, 2):
+                cols.append(torch.where(a[..., f] < 0, dt[..., 2 * c + (n - 1)], d[..., f]))
+            else:
+                cols.append(d[..., f])
+        out.append(symnet_apply(torch.stack(cols, dim=-1), symnet[co], L))
+    return torch.stack(out, dim=1)
+
+
+def upwind_step(u, Ks, symnet, L, dt):
+    return u + dt * upwind_right_hand_items(u, Ks, symnet, L)
+
+
+def upwind_rollout(u0, Ks, symnet, L, dt, steps: int):
+    states, u = [], u0
+    for _ in range(steps):
+        u = upwind_step(u, Ks, symnet, L, dt)
         states.append(u)
     return states
 

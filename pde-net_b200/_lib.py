@@ -34,6 +34,12 @@ _PROTOS = {
     "pdenet_rollout_bwd_needs_features": (_i, [_i] * 5),
     "pdenet_rhs_fwd_{t}": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "pdenet_rhs_bwd_{t}": (_i, [_vp] * 8 + [_sz] + [_i] * 8 + [_vp]),
+    "pdenet_upwind_supported": (_i, [_i] * 5),
+    "pdenet_rollout_fwd_upwind_{t}": (_i, [_vp] * 4 + [_i] * 8 + [_d, _vp]),
+    "pdenet_rollout_bwd_upwind_workspace_bytes": (_sz, [_i] * 9),
+    "pdenet_rollout_bwd_upwind_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
+    "pdenet_rhs_upwind_fwd_{t}": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
+    "pdenet_rhs_upwind_bwd_{t}": (_i, [_vp] * 8 + [_sz] + [_i] * 8 + [_vp]),
     "pdenet_rollout_fwd_keep_{t}": (_i, [_vp] * 5 + [_i] * 8 + [_d, _vp]),
     "pdenet_rollout_bwd_kept_{t}": (_i, [_vp, _vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
     "pdenet_rollout_bwd_workspace_bytes": (_sz, [_i] * 9),

@@ -296,6 +296,46 @@ static int upload(const SlotLease &lease, const T *k0, const T *taps, int n, int
   return rc;
 }
 
+// ---- pseudo-upwind bank (row f-1): bank order puts order (0,1) at index 1 (derivative along W) and
+// (1,0) at index 2 (along H); their flipped twins  K1-[a,b] = -K1[a,k-1-b],  K2-[a,b] = -K2[k-1-a,b]
+// (mirror along the derivative axis, negate: the same derivative with the opposite bias) follow the
+// N central filters.  The twins of a call are built in a per-slot device scratch and uploaded from there.
+__device__ __align__(16) unsigned char g_upwind_scratch[kConstSlots][2 * PDENET_MAX_K * PDENET_MAX_K * 8];
+
+template <typename T> __global__ void upwind_twins_kernel(const T *kernels, int k, T *twins) {
+  const int t = threadIdx.x, kk = k * k;
+  if (t >= 2 * kk) return;
+  const int which = t / kk, e = t % kk, a = e / k, b = e % k;
+  twins[t] = which == 0 ? -kernels[1 * kk + a * k + (k - 1 - b)] : -kernels[2 * kk + (k - 1 - a) * k + b];
+}
+// grad[n] = dk[n] (n < N) minus the mirrored gradient of the twin for n = 1, 2
+template <typename T> __global__ void upwind_fold_kernel(const T *dk_bank, int N, int k, T *grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, kk = k * k;
+  if (i >= N * kk) return;
+  const int n = i / kk, e = i % kk, a = e / k, b = e % k;
+  T v = dk_bank[i];
+  if (n == 1) v -= dk_bank[N * kk + a * k + (k - 1 - b)];
+  if (n == 2) v -= dk_bank[(N + 1) * kk + (k - 1 - a) * k + b];
+  grad[i] = v;
+}
+static bool upwind_supported(int N, int C) { return (N == 3 || N == 6) && (C == 1 || C == 2); }
+
+// upload the N central filters followed by the two twins into the leased slot
+template <typename T>
+static int upload_upwind(const SlotLease &lease, const T *kernels, int N, int k, cudaStream_t st) {
+  if (lease.slot < 0) return PDENET_E_CUDA;
+  void *scr = nullptr;
+  if (cudaGetSymbolAddress(&scr, g_upwind_scratch) != cudaSuccess) return PDENET_E_CUDA;
+  T *twins = (T *)((unsigned char *)scr + (size_t)lease.slot * sizeof(g_upwind_scratch[0]));
+  upwind_twins_kernel<T><<<1, 128, 0, st>>>(kernels, k, twins);
+  if (cudaGetLastError() != cudaSuccess) return PDENET_E_CUDA;
+  int rc = 0;
+  PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, 0, kernels, N, st)));
+  if (rc) return rc;
+  PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, N, twins, 2, st)));
+  return rc;
+}
+
 static bool bad_geom(int B, int C, int H, int W, int k, int N) {
   return B <= 0 || C <= 0 || H <= 0 || W <= 0 || k <= 0 || (k % 2) == 0 || N <= 0;
 }
@@ -307,7 +347,9 @@ static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int
   p.W = W;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  ProfScope ps((mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT || mode == MODE_LIN_BWD_A) ? 1 : 0, st);
+  ProfScope ps((mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT || mode == MODE_LIN_BWD_A || mode == MODE_UPW_BWD_A) ? 1
+                                                                                                                  : 0,
+               st);
   return launch_step<T, K>(mode, N, C, VL, p, sms, st);
 }
 
@@ -374,13 +416,19 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
 // ---- forward rollout (rows a5-a10) -----------------------------------------------------------
 template <typename T>
 static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states, T *feats, int B, int C, int H,
-                       int W, int k, int N, int L, int steps, double dt, void *stream, int rhs_only = 0) {
+                       int W, int k, int N, int L, int steps, double dt, void *stream, int rhs_only = 0,
+                       bool upwind = false) {
   if (!u0 || !kernels || !symnet || !states || bad_geom(B, C, H, W, k, N) || L < 0 || steps < 0)
     return PDENET_E_BADARG;
-  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C) || (upwind && (!upwind_supported(N, C) || feats)))
+    return PDENET_E_UNSUPPORTED;
   const size_t stride = (size_t)B * C * H * W;
   SlotLease lease((cudaStream_t)stream);
-  if (int rc = upload<T>(lease, nullptr, kernels, N, k, (cudaStream_t)stream)) return rc;
+  if (upwind) {
+    if (int rc = upload_upwind<T>(lease, kernels, N, k, (cudaStream_t)stream)) return rc;
+  } else if (int rc = upload<T>(lease, nullptr, kernels, N, k, (cudaStream_t)stream)) {
+    return rc;
+  }
   StepParams<T> p;
   memset(&p, 0, sizeof(p));
   p.slot = lease.slot;
@@ -396,7 +444,11 @@ static int rollout_fwd(const T *u0, const T *kernels, const T *symnet, T *states
     p.out = states + (size_t)t * stride;
     p.feats = feats ? feats + (size_t)t * stride * N : nullptr; // features of the step's input state u_t
     int rc = 0;
-    PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, H, W, (cudaStream_t)stream)));
+    if (upwind) {
+      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_UPW_FWD, N + 2, C, 16, p, B, H, W, (cudaStream_t)stream)));
+    } else {
+      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(MODE_FWD, N, C, 16, p, B, H, W, (cudaStream_t)stream)));
+    }
     if (rc) return rc;
   }
   return PDENET_OK;
@@ -637,7 +689,7 @@ static int slab_bwd_end(void *workspace, size_t ws_bytes, T *grad_kernels, T *gr
 
 // ---- reverse rollout (row a11) ---------------------------------------------------------------
 struct BwdLayout {
-  size_t off_g, off_lam0, off_lam1, off_dk, off_sym, total;
+  size_t off_g, off_lam0, off_lam1, off_dk, off_sym, off_bank, total;
   int chunk, dk_slots, sym_slots, vlb;
 };
 
@@ -660,7 +712,17 @@ static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N,
   o = align_up(o + (size_t)l.dk_slots * N * l.vlb * sizeof(double), 256);
   l.off_sym = o;
   o = align_up(o + (size_t)l.sym_slots * C * symnet_param_count(C * N, L) * sizeof(double), 256);
+  l.off_bank = o; // upwind: gradient of the whole bank (N filters incl. the twins) before it is folded
+  o = align_up(o + (size_t)N * kk * es, 256);
   l.total = o;
+  return l;
+}
+
+// upwind: g / dK regions for the bank of Ns + 2 filters, SymNet partials for C*Ns inputs
+static BwdLayout bwd_layout_upwind(size_t es, int B, int C, int H, int W, int k, int Ns, int L, int batch_chunk,
+                                   int sms) {
+  BwdLayout l = bwd_layout(es, B, C, H, W, k, Ns + 2, L, batch_chunk, sms);
+  // the SymNet region of the wide layout is an upper bound of what C*Ns inputs need: keep it
   return l;
 }
 
@@ -668,17 +730,21 @@ template <typename T>
 static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *grad_states, int grad_mode,
                        const T *kernels, const T *symnet, T *grad_u0, T *grad_kernels, T *grad_symnet, void *workspace,
                        size_t ws_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L, int steps,
-                       double dt, void *stream, bool identity = true) {
+                       double dt, void *stream, bool identity = true, bool upwind = false) {
   if (!u0 || !grad_states || !kernels || !symnet || !workspace || bad_geom(B, C, H, W, k, N) || L < 0 ||
       steps < 1 || (steps > 1 && !states) || (grad_mode != PDENET_GRAD_LAST && grad_mode != PDENET_GRAD_ALL))
     return PDENET_E_BADARG;
-  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C)) return PDENET_E_UNSUPPORTED;
+  if (L > PDENET_MAX_LAYERS || !nc_supported(N, C) || (upwind && (!upwind_supported(N, C) || feats)))
+    return PDENET_E_UNSUPPORTED;
+  const int Ns = N;            // filters feeding the SymNet
+  if (upwind) N += 2;          // the bank the stencil / data-gradient / filter-gradient kernels see
   const int M = C * N;
-  const int VL = pick_vl(M, L);
+  const int VL = pick_vl(C * Ns, L);
   if (!VL) return PDENET_E_UNSUPPORTED;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
+  // (upwind: sized for the bank of Ns + 2 filters == bwd_layout_upwind(Ns))
   const BwdLayout lay = bwd_layout(sizeof(T), B, C, H, W, k, N, L, batch_chunk, sms);
   if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
   char *ws = (char *)workspace;
@@ -686,13 +752,17 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
   T *lamb[2] = {(T *)(ws + lay.off_lam0), (T *)(ws + lay.off_lam1)};
   double *dkp = (double *)(ws + lay.off_dk);
   double *symp = (double *)(ws + lay.off_sym);
-  const int Psym = symnet_param_count(M, L);
+  const int Psym = symnet_param_count(C * Ns, L);
   if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * N * lay.vlb * sizeof(double), st) != cudaSuccess ||
       cudaMemsetAsync(symp, 0, (size_t)lay.sym_slots * C * Psym * sizeof(double), st) != cudaSuccess)
     return PDENET_E_CUDA;
 
   SlotLease lease(st);
-  if (int rc = upload<T>(lease, nullptr, kernels, N, k, st)) return rc;
+  if (upwind) {
+    if (int rc = upload_upwind<T>(lease, kernels, Ns, k, st)) return rc;
+  } else if (int rc = upload<T>(lease, nullptr, kernels, N, k, st)) {
+    return rc;
+  }
   const size_t img = (size_t)H * W;
   const size_t stride = (size_t)B * C * img;
   const T *lam_in = grad_mode == PDENET_GRAD_ALL ? grad_states + (size_t)(steps - 1) * stride : grad_states;
@@ -722,7 +792,8 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
       // kept features of u_t (forward ran with a feature buffer): kernel A skips the stencils
       p.feats = feats ? const_cast<T *>(feats) + ((size_t)t * B + b0) * M * img : nullptr;
       int rc = 0;
-      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(feats ? MODE_BWD_A_KEPT : MODE_BWD_A, N, C, VL, p, nb, H, W, st)));
+      PDENET_DISPATCH_K(k, rc = (run_step<T, KK_>(upwind ? MODE_UPW_BWD_A : (feats ? MODE_BWD_A_KEPT : MODE_BWD_A), N, C,
+                                                  VL, p, nb, H, W, st)));
       if (rc) return rc;
       if (lam_out) {
         AdjParams<T> q;
@@ -760,7 +831,10 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
   if (grad_kernels) {
     const int n = N * k * k;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, grad_kernels);
+    T *bank = upwind ? (T *)(ws + lay.off_bank) : grad_kernels;
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, bank);
+    if (upwind) // dK of a twin is the mirrored, negated contribution to its central filter
+      upwind_fold_kernel<T><<<(Ns * k * k + 127) / 128, 128, 0, st>>>(bank, Ns, k, grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * Psym;
@@ -1288,6 +1362,65 @@ int pdenet_rhs_bwd_f32(const float *u, const float *grad_out, const float *kerne
   return rollout_bwd<float>(u, nullptr, nullptr, grad_out, PDENET_GRAD_LAST, kernels, symnet, grad_u, grad_kernels,
                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, 1, 1.0, st,
                             false);
+}
+
+int pdenet_rollout_fwd_upwind_f64(const double *u0, const double *kernels, const double *symnet, double *states, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_fwd<double>(u0, kernels, symnet, states, nullptr, B, C, H, W, k, N, L, steps, dt, st, 0, true);
+}
+int pdenet_rollout_fwd_upwind_f32(const float *u0, const float *kernels, const float *symnet, float *states, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_fwd<float>(u0, kernels, symnet, states, nullptr, B, C, H, W, k, N, L, steps, dt, st, 0, true);
+}
+int pdenet_rhs_upwind_fwd_f64(const double *u, const double *kernels, const double *symnet, double *out, int B, int C,
+                              int H, int W, int k, int N, int L, void *st) {
+  return rollout_fwd<double>(u, kernels, symnet, out, nullptr, B, C, H, W, k, N, L, 1, 1.0, st, 1, true);
+}
+int pdenet_rhs_upwind_fwd_f32(const float *u, const float *kernels, const float *symnet, float *out, int B, int C,
+                              int H, int W, int k, int N, int L, void *st) {
+  return rollout_fwd<float>(u, kernels, symnet, out, nullptr, B, C, H, W, k, N, L, 1, 1.0, st, 1, true);
+}
+size_t pdenet_rollout_bwd_upwind_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,
+                                                 int batch_chunk) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, C, H, W, k, N) || L < 0 || !upwind_supported(N, C)) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  return bwd_layout_upwind((size_t)elem_size, B, C, H, W, k, N, L, batch_chunk, sms).total;
+}
+int pdenet_rollout_bwd_upwind_f64(const double *u0, const double *states, const double *grad_states, int grad_mode,
+                                  const double *kernels, const double *symnet, double *grad_u0, double *grad_kernels,
+                                  double *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_bwd<double>(u0, states, nullptr, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st,
+                             true, true);
+}
+int pdenet_rollout_bwd_upwind_f32(const float *u0, const float *states, const float *grad_states, int grad_mode,
+                                  const float *kernels, const float *symnet, float *grad_u0, float *grad_kernels,
+                                  float *grad_symnet, void *workspace, size_t workspace_bytes, int batch_chunk, int B,
+                                  int C, int H, int W, int k, int N, int L, int steps, double dt, void *st) {
+  return rollout_bwd<float>(u0, states, nullptr, grad_states, grad_mode, kernels, symnet, grad_u0, grad_kernels,
+                            grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, steps, dt, st,
+                            true, true);
+}
+int pdenet_rhs_upwind_bwd_f64(const double *u, const double *grad_out, const double *kernels, const double *symnet,
+                              double *grad_u, double *grad_kernels, double *grad_symnet, void *workspace,
+                              size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                              void *st) {
+  return rollout_bwd<double>(u, nullptr, nullptr, grad_out, PDENET_GRAD_LAST, kernels, symnet, grad_u, grad_kernels,
+                             grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, 1, 1.0, st,
+                             false, true);
+}
+int pdenet_rhs_upwind_bwd_f32(const float *u, const float *grad_out, const float *kernels, const float *symnet,
+                              float *grad_u, float *grad_kernels, float *grad_symnet, void *workspace,
+                              size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
+                              void *st) {
+  return rollout_bwd<float>(u, nullptr, nullptr, grad_out, PDENET_GRAD_LAST, kernels, symnet, grad_u, grad_kernels,
+                            grad_symnet, workspace, workspace_bytes, batch_chunk, B, C, H, W, k, N, L, 1, 1.0, st,
+                            false, true);
+}
+int pdenet_upwind_supported(int elem_size, int k, int N, int C, int L) {
+  return pdenet_supported(elem_size, k, N, C, L) && upwind_supported(N, C) ? 1 : 0;
 }
 
 size_t pdenet_rollout_bwd_workspace_bytes(int elem_size, int B, int C, int H, int W, int k, int N, int L,

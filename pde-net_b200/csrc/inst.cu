@@ -26,7 +26,7 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
   p.n_items = p.B * p.tiles_x * p.tiles_y;
   const int grid = p.n_items < sms ? p.n_items : sms;
-  constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT;
+  constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT || MODE == MODE_UPW_BWD_A;
   const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);
   if (smem > kMaxDynamicSmem) return -2; // e.g. 3-channel banks with deep SymNets in the recomputing reverse kernel
   auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
@@ -60,6 +60,23 @@ int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms,
     }                                                                                                            \
   }
   PDENET_FOR_NC(PDENET_CASE)
+#undef PDENET_CASE
+  // pseudo-upwind: NN = bank size incl. the two flipped twins, the SymNet sees CC*(NN-2) inputs
+#define PDENET_CASE(NN, CC)                                                                                       \
+  if (N == NN && C == CC) {                                                                                      \
+    if (mode == MODE_UPW_FWD) {                                                                                  \
+      if (p.L == 2) return launch_step_one<T, K, NN, CC, MODE_UPW_FWD, 16, 2>(p, sms, st);                       \
+      return launch_step_one<T, K, NN, CC, MODE_UPW_FWD, 16>(p, sms, st);                                        \
+    }                                                                                                            \
+    if (mode == MODE_UPW_BWD_A) {                                                                                \
+      if constexpr ((NN - 2) * CC + 3 <= 16)                                                                     \
+        if (VL == 16 && p.L == 2) return launch_step_one<T, K, NN, CC, MODE_UPW_BWD_A, 16, 2>(p, sms, st);       \
+      if constexpr ((NN - 2) * CC + 1 < 16)                                                                      \
+        if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_UPW_BWD_A, 16>(p, sms, st);                     \
+      if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_UPW_BWD_A, 32>(p, sms, st);                       \
+    }                                                                                                            \
+  }
+  PDENET_FOR_UPW(PDENET_CASE)
 #undef PDENET_CASE
 #define PDENET_CASE(NN)                                                                                           \
   if (N == NN && C == 1) {                                                                                       \

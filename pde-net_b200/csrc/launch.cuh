@@ -7,6 +7,9 @@ namespace pdenet {
 // (N filters, C channels) pairs compiled for the SymNet (PDE-Net 2.0) kernels: max_order 1..4
 // with up to 3 state channels, bounded by the register budget for the C*N features per point.
 #define PDENET_FOR_NC(X) X(1, 1) X(3, 1) X(3, 2) X(3, 3) X(6, 1) X(6, 2) X(6, 3) X(10, 1) X(15, 1)
+// (bank size incl. the two flipped first-order twins, C channels) compiled for the pseudo-upwind scheme
+// (row f-1): max_order 1..2 with up to 2 state channels
+#define PDENET_FOR_UPW(X) X(5, 1) X(5, 2) X(8, 1) X(8, 2)
 // filter counts (incl. the order-(0,0) filter D0) compiled for the linear (PDE-Net 1) kernels: max_order 1..4
 #define PDENET_FOR_LIN(X) X(3) X(6) X(10) X(15)
 

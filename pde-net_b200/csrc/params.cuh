@@ -10,8 +10,14 @@ enum StepMode {
   MODE_BWD_A = 2,
   MODE_LIN_FWD = 3,
   MODE_LIN_BWD_A = 4,
-  MODE_BWD_A_KEPT = 5 // reverse kernel A reading the features the forward step kept (no stencil recompute)
+  MODE_BWD_A_KEPT = 5, // reverse kernel A reading the features the forward step kept (no stencil recompute)
+  // pseudo-upwind scheme (row f-1): the bank carries two extra filters per channel, the flipped
+  // first-order filters, as its last two entries; per output channel and grid point the SymNet sees
+  // either a first-order feature or its flipped twin, chosen by the sign of d SymNet / d feature
+  MODE_UPW_FWD = 6,
+  MODE_UPW_BWD_A = 7
 };
+__host__ __device__ constexpr bool mode_is_upwind(int mode) { return mode == MODE_UPW_FWD || mode == MODE_UPW_BWD_A; }
 
 template <typename T> struct StepParams {
   // input state [B][C][u_rows][W]
@@ -48,7 +54,8 @@ template <typename T> struct StepParams {
 // Threads per CTA: the forward-type kernels fit 168 registers when C*N <= 12, so they run 12
 // warps per SM; the reverse kernel A (and the widest banks) need up to 255 registers -> 8 warps.
 __host__ __device__ constexpr int step_threads(int mode, int M) {
-  return ((mode == MODE_FWD || mode == MODE_FEATS || mode == MODE_LIN_FWD) && M <= 12) ? 384 : 256;
+  return ((mode == MODE_FWD || mode == MODE_FEATS || mode == MODE_LIN_FWD || mode == MODE_UPW_FWD) && M <= 12) ? 384
+                                                                                                               : 256;
 }
 
 template <typename T> struct AdjParams {

@@ -53,8 +53,9 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
 // the few per-layer scalars (p, q, product units) live in small local arrays.
 // LT >= 0: the depth is a compile-time constant (layer loops fully unrolled, parameter offsets become
 // immediates, the per-layer scalars stay in registers); LT < 0: run-time depth L_rt.
-template <typename T, int M, int P, int PP, int J0, bool KEEP, int LT, bool NEED_OUT = true>
-__device__ __forceinline__ int symnet_forward(const T (&d)[M][P], const T *prm, int L_rt, T (&out)[PP],
+// MD (deduced) >= M: the feature array may carry extra rows after the M SymNet inputs (upwind twins).
+template <typename T, int M, int P, int PP, int J0, bool KEEP, int LT, bool NEED_OUT = true, int MD = M>
+__device__ __forceinline__ int symnet_forward(const T (&d)[MD][P], const T *prm, int L_rt, T (&out)[PP],
                                               T (*un)[PP], T (*pl)[PP], T (*ql)[PP]) {
   const int L = LT >= 0 ? LT : L_rt;
   int off = 0;
@@ -142,8 +143,8 @@ template <typename T, int NE> __device__ __forceinline__ T transpose_sum(const T
 // features) over output channels and reduces the parameter gradients (rows a7/a11).
 // VL (16 or 32) >= M + L + 1 is the padded length of one parameter-gradient vector
 // [features 0..M), product units [M..M+L), bias at VL-1].
-template <typename T, int M, int P, int PP, int J0, int VL, int C, int LT>
-__device__ __forceinline__ void symnet_reverse(const T (&d)[M][P], const T *syms, int Psym, int L_rt,
+template <typename T, int M, int P, int PP, int J0, int VL, int C, int LT, int MD = M>
+__device__ __forceinline__ void symnet_reverse(const T (&d)[MD][P], const T *syms, int Psym, int L_rt,
                                                const T (&lamv)[C][PP], T (&gacc)[M][PP], double *sg, T *scratch) {
   const int L = LT >= 0 ? LT : L_rt;
   constexpr int UCAP = (VL - 1 - M) < kMaxLayers ? (VL - 1 - M) : kMaxLayers; // static bound on L
@@ -507,6 +508,136 @@ __device__ __forceinline__ void reverse_half(const T (&d)[M][P], const T *syms, 
 }
 
 // --------------------------------------------------------------------------------------------
+// Pseudo-upwind selection (row f-1; restated from the description of arXiv 1812.04426, see the
+// header include/pdenet_b200.h for the conventions).  Register layout of the feature array in the
+// upwind modes: rows [0, MS) are the SymNet inputs f = c*NC + n (NC central filters per channel),
+// rows MS + 2c + dir are the flipped twins of channel c's first-order filters (dir 0: order (0,1),
+// bank index 1; dir 1: order (1,0), bank index 2).  For output channel `co` the local "velocity" of
+// input (c, dir) is a = d SymNet_co / d x_f at the CENTRAL features; a < 0 selects the flipped twin.
+// upwind_select evaluates a for PP points, swaps the selected twins INTO the SymNet rows (so the
+// unchanged SymNet code sees the selected inputs) and returns the masks; calling upwind_swap with
+// the same masks restores the array.
+template <typename T, int MS, int C, int NC, int P, int PP, int J0, int MD>
+__device__ __forceinline__ void upwind_swap(T (&d)[MD][P], const bool (&mask)[2 * C][PP]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir)
+#pragma unroll
+      for (int jj = 0; jj < PP; ++jj) {
+        const T a = d[c * NC + 1 + dir][J0 + jj], b = d[MS + 2 * c + dir][J0 + jj];
+        d[c * NC + 1 + dir][J0 + jj] = mask[2 * c + dir][jj] ? b : a;
+        d[MS + 2 * c + dir][J0 + jj] = mask[2 * c + dir][jj] ? a : b;
+      }
+}
+
+template <typename T, int MS, int C, int NC, int P, int PP, int J0, int LT, int MD>
+__device__ __forceinline__ void upwind_select(T (&d)[MD][P], const T *prm, int L_rt, bool (&mask)[2 * C][PP]) {
+  const int L = LT >= 0 ? LT : L_rt;
+  T un[kMaxLayers][PP], pl[kMaxLayers][PP], ql[kMaxLayers][PP], eta[kMaxLayers][PP], fout[PP];
+  const int off_f = symnet_forward<T, MS, P, PP, J0, true, LT, false>(d, prm, L, fout, un, pl, ql);
+  // eta_i = d out / d unit_i, then pl/ql are overwritten with d out / d p_i, d out / d q_i
+#pragma unroll(LT >= 0 ? 8 : 1)
+  for (int i2 = 0; i2 < L; ++i2) {
+    const T wf = prm[off_f + MS + i2];
+#pragma unroll
+    for (int jj = 0; jj < PP; ++jj) eta[i2][jj] = wf;
+  }
+  int off = off_f;
+#pragma unroll(LT >= 0 ? 8 : 1)
+  for (int i = L - 1; i >= 0; --i) {
+    const int mi = MS + i;
+    off -= 2 * mi + 2;
+#pragma unroll
+    for (int jj = 0; jj < PP; ++jj) {
+      const T pb = eta[i][jj] * ql[i][jj], qb = eta[i][jj] * pl[i][jj];
+      pl[i][jj] = pb;
+      ql[i][jj] = qb;
+    }
+#pragma unroll(LT >= 0 ? 8 : 1)
+    for (int i2 = 0; i2 < i; ++i2) {
+      const T w0 = prm[off + MS + i2], w1 = prm[off + mi + MS + i2];
+#pragma unroll
+      for (int jj = 0; jj < PP; ++jj) eta[i2][jj] = fma_(pl[i][jj], w0, fma_(ql[i][jj], w1, eta[i2][jj]));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+      const int f = c * NC + 1 + dir;
+      T a[PP];
+#pragma unroll
+      for (int jj = 0; jj < PP; ++jj) a[jj] = prm[off_f + f];
+      int o2 = 0;
+#pragma unroll(LT >= 0 ? 8 : 1)
+      for (int i = 0; i < L; ++i) {
+        const int mi = MS + i;
+        const T w0 = prm[o2 + f], w1 = prm[o2 + mi + f];
+#pragma unroll
+        for (int jj = 0; jj < PP; ++jj) a[jj] = fma_(pl[i][jj], w0, fma_(ql[i][jj], w1, a[jj]));
+        o2 += 2 * mi + 2;
+      }
+#pragma unroll
+      for (int jj = 0; jj < PP; ++jj) mask[2 * c + dir][jj] = a[jj] < T(0);
+    }
+  upwind_swap<T, MS, C, NC, P, PP, J0>(d, mask);
+}
+
+// One half-strip (2 points) of the upwind reverse kernel: per output channel select, SymNet reverse on
+// the selected inputs, scatter g to the central / flipped planes (first channel stores, later ones add).
+template <typename T, int MS, int C, int NC, int P, int J0, int VL, int LT, int MD>
+__device__ __forceinline__ void upwind_reverse_half(T (&d)[MD][P], const T *syms, int Psym, int L,
+                                                    const bool (&valid)[P], const T (&lam_raw)[C][P],
+                                                    const StepParams<T> &p, int b, int y0, int x, double *sgrad_warp,
+                                                    T *scratch) {
+  constexpr int PP = 2, NF = NC + 2;
+  const int W = p.W;
+  const size_t plane = (size_t)p.g_rows * W;
+  T *g0 = p.g + ((size_t)b * (C * NF) * p.g_rows + (y0 + J0 + p.g_off)) * W + x;
+#pragma unroll 1
+  for (int co = 0; co < C; ++co) {
+    const T *prm = syms + co * Psym;
+    bool mask[2 * C][PP];
+    upwind_select<T, MS, C, NC, P, PP, J0, LT>(d, prm, L, mask);
+    T lamv[1][PP];
+#pragma unroll
+    for (int jj = 0; jj < PP; ++jj) {
+      T lv = T(0);
+#pragma unroll
+      for (int c2 = 0; c2 < C; ++c2) lv = (c2 == co) ? lam_raw[c2][J0 + jj] : lv;
+      lamv[0][jj] = p.dt * lv;
+    }
+    T gacc[MS][PP];
+    symnet_reverse<T, MS, P, PP, J0, VL, 1, LT>(d, prm, Psym, L, lamv, gacc, sgrad_warp + co * Psym, scratch);
+    // g planes in bank order: channel c, filter n -> plane c*NF + n (n >= NC: flipped twins)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int n = 0; n < NF; ++n) {
+        T *gp = g0 + (size_t)(c * NF + n) * plane;
+#pragma unroll
+        for (int jj = 0; jj < PP; ++jj) {
+          T v;
+          if (n >= NC)
+            v = mask[2 * c + (n - NC)][jj] ? gacc[c * NC + 1 + (n - NC)][jj] : T(0);
+          else if (n == 1 || n == 2)
+            v = mask[2 * c + (n - 1)][jj] ? T(0) : gacc[c * NC + n][jj];
+          else
+            v = gacc[c * NC + n][jj];
+          if (valid[J0 + jj]) {
+            if (co == 0)
+              gp[(size_t)jj * W] = v;
+            else
+              gp[(size_t)jj * W] += v;
+          }
+        }
+      }
+    upwind_swap<T, MS, C, NC, P, PP, J0>(d, mask);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 template <typename T, int K, int N, int C, int MODE, int VL, int LT>
 __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const StepParams<T> p) {
   using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
@@ -514,7 +645,10 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
   constexpr bool KEPT = (MODE == MODE_BWD_A_KEPT); // features come from HBM: no tile staging, no block barrier
-  constexpr bool WITH_GRAD = (MODE == MODE_BWD_A || KEPT);
+  constexpr bool UPW = mode_is_upwind(MODE);      // bank = NC central filters + the 2 flipped first-order twins
+  constexpr bool WITH_GRAD = (MODE == MODE_BWD_A || KEPT || MODE == MODE_UPW_BWD_A);
+  constexpr int NC = UPW ? N - 2 : N;             // filters feeding the SymNet per channel
+  constexpr int MS = C * NC;                      // SymNet inputs (== M unless upwind)
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sgrad = reinterpret_cast<double *>(smem_raw); // [NT/32][grad_elems]  (MODE_BWD_A only)
@@ -552,7 +686,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
   constexpr int region = Cfg::tile_region(KEPT);
   T *scratch = tiles + region + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (reverse)
   int *rev_tables = reinterpret_cast<int *>(tiles + region + (NT / 32) * TransposeCfg<T>::ELEMS);
-  constexpr bool REV_FULL = WITH_GRAD && RevFullCfg<M, C, LT>::OK;
+  constexpr bool REV_FULL = WITH_GRAD && !UPW && RevFullCfg<M, C, LT>::OK;
   if constexpr (REV_FULL) {
     if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
   }
@@ -653,7 +787,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
 #pragma unroll
         for (int n = 0; n < N; ++n)
 #pragma unroll
-          for (int j = 0; j < P; ++j) d[c * N + n][j] = acc[n][j];
+          for (int j = 0; j < P; ++j) d[UPW ? (n < NC ? c * NC + n : MS + 2 * c + (n - NC)) : c * N + n][j] = acc[n][j];
         if constexpr (MODE == MODE_FWD) {
           // keep this channel's features for the reverse pass (written once, read once: streaming
           // stores); issued per channel, while few registers are live, with 32-bit row offsets
@@ -696,6 +830,28 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
                 if (y >= H - p.mirror_rows) p.peer_dn[(img + p.out_off + y - H) * W + x] = v;
               }
             }
+        }
+      } else if constexpr (MODE == MODE_UPW_FWD) {
+        // ---- pseudo-upwind step (row f-1): per output channel select the first-order inputs, SymNet, Euler
+#pragma unroll 1
+        for (int co = 0; co < C; ++co) {
+          bool mask[2 * C][P];
+          upwind_select<T, MS, C, NC, P, P, 0, LT>(d, syms + co * Psym, L, mask);
+          T un[kMaxLayers][P], fout[P];
+          symnet_forward<T, MS, P, P, 0, false, LT>(d, syms + co * Psym, L, fout, un, un, un);
+          upwind_swap<T, MS, C, NC, P, P, 0>(d, mask);
+          const T *uc = tile + (co * SR + row0 + R) * PITCH + col + R;
+          T *op = p.out + ((size_t)(b * C + co) * p.out_rows + (y0 + p.out_off)) * W + x;
+#pragma unroll
+          for (int j = 0; j < P; ++j)
+            if (valid[j]) op[(size_t)j * W] = p.rhs_only ? fout[j] : fma_(p.dt, fout[j], uc[j * PITCH]);
+        }
+      } else if constexpr (MODE == MODE_UPW_BWD_A) {
+        upwind_reverse_half<T, MS, C, NC, P, 0, VL, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        upwind_reverse_half<T, MS, C, NC, P, 2, VL, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+        if constexpr (P == 8) {
+          upwind_reverse_half<T, MS, C, NC, P, 4, VL, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
+          upwind_reverse_half<T, MS, C, NC, P, 6, VL, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
         }
       } else if constexpr (WITH_GRAD && !LINEAR) {
         // ---- SymNet reverse, two points at a time (register budget), rows a7/a11

@@ -161,13 +161,16 @@ class poly(nn.Module):
 
 
 class POLYPDE2D(nn.Module):
-    """PDE-Net 2.0 model (rows a8-a10): ``forward(init, T)`` = state after ``round(T/dt)`` Euler steps."""
+    """PDE-Net 2.0 model (rows a8-a10): ``forward(init, T)`` = state after ``round(T/dt)`` Euler steps.
+    ``scheme``: ``'central'`` or ``'upwind'`` (pseudo-upwind first-order inputs, row f-1; supported for
+    ``max_order`` 1-2 and up to two channels)."""
 
     def __init__(self, dt, dx, kernel_size, max_order, constraint, channel_names, hidden_layers=2,
                  scheme="central", dtype=torch.float64, batch_chunk=0, keep_features=None):
         super().__init__()
-        if scheme != "central":
-            raise NotImplementedError("scheme=%r: only the central scheme is on the B200 hot path" % scheme)
+        if scheme not in ("central", "upwind"):
+            raise ValueError("scheme must be 'central' or 'upwind', got %r" % (scheme,))
+        self.scheme = scheme
         self.dt, self.dx = float(dt), _pair(dx)
         self.kernel_size, self.max_order, self.constraint = kernel_size, max_order, constraint
         self.channel_names = list(channel_names.split(",")) if isinstance(channel_names, str) else list(channel_names)
@@ -234,7 +237,8 @@ class POLYPDE2D(nn.Module):
     def RightHandItems(self, u: torch.Tensor) -> torch.Tensor:
         """F(u) [B,C,H,W]: the fused step kernel writing the SymNet output itself (no Euler update,
         no differencing of states)."""
-        return ops.rhs(u, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.batch_chunk)
+        return ops.rhs(u, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.batch_chunk,
+                       scheme=self.scheme)
 
     def predict(self, u: torch.Tensor) -> torch.Tensor:
         """One forward-Euler step ``u + dt*F(u)``."""
@@ -247,7 +251,7 @@ class POLYPDE2D(nn.Module):
             raise ValueError("stepnum must be a positive integer, got %r" % (stepnum,))
         return ops.rollout(inputs, self.scaled_kernels(), self.symnet_flat(), self.hidden_layers, self.dt,
                            int(stepnum), last_only=not all_states, batch_chunk=self.batch_chunk,
-                           keep_features=self.keep_features)
+                           keep_features=self.keep_features, scheme=self.scheme)
 
     def forward(self, init: torch.Tensor, T: float, all_states: bool = False) -> torch.Tensor:
         """State after time ``T``; ``T`` must be a whole number of steps of ``dt`` (as upstream, which

@@ -155,7 +155,7 @@ FEATURE_CACHE_BYTES = int(float(os.environ.get("PDENET_FEATURE_CACHE_GB", "32"))
 
 class _Rollout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk, keep_features):
+    def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk, keep_features, upwind=False):
         u0 = _req(u0, "u0")
         kernels = _req(kernels, "kernels", u0.dtype)
         symnet = _req(symnet, "symnet", u0.dtype)
@@ -165,6 +165,19 @@ class _Rollout(torch.autograd.Function):
             raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
         states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
+        ctx.upwind = bool(upwind)
+        if upwind:   # pseudo-upwind scheme (row f-1): features are always recomputed by the reverse pass
+            _lib.check(_lib.fn("pdenet_rollout_fwd_upwind", u0.dtype)(
+                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
+                _stream()), "pdenet_rollout_fwd_upwind")
+            ctx.feats = None
+            ctx.cfg = (L, float(dt), steps, last_only, batch_chunk)
+            if last_only:
+                ctx.save_for_backward(u0, kernels, symnet)
+                ctx.states = states
+                return states[-1]
+            ctx.save_for_backward(u0, kernels, symnet, states)
+            return states
         feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
         auto = keep_features is None
         if auto:
@@ -209,14 +222,21 @@ class _Rollout(torch.autograd.Function):
         N, k, _ = kernels.shape
         grad = _req(grad, "grad_states", u0.dtype)
         es = u0.element_size()
-        nbytes = _lib.lib().pdenet_rollout_bwd_workspace_bytes(es, B, Cc, H, W, k, N, L, batch_chunk)
+        wsfn = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes if ctx.upwind \
+            else _lib.lib().pdenet_rollout_bwd_workspace_bytes
+        nbytes = wsfn(es, B, Cc, H, W, k, N, L, batch_chunk)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
         need_u, need_k, need_s = ctx.needs_input_grad[:3]
         gu = torch.empty_like(u0) if need_u else None
         gk = torch.empty_like(kernels) if need_k else None
         gs = torch.empty_like(symnet) if need_s else None
         mode = _lib.GRAD_LAST if last_only else _lib.GRAD_ALL
-        if ctx.feats is not None:
+        if ctx.upwind:
+            _lib.check(_lib.fn("pdenet_rollout_bwd_upwind", u0.dtype)(
+                _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
+                _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
+                "pdenet_rollout_bwd_upwind")
+        elif ctx.feats is not None:
             _lib.check(_lib.fn("pdenet_rollout_bwd_kept", u0.dtype)(
                 _ptr(u0), _ptr(states), _ptr(ctx.feats), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu),
                 _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
@@ -225,11 +245,17 @@ class _Rollout(torch.autograd.Function):
             _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
                 _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
                 _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()), "pdenet_rollout_bwd")
-        return gu, gk, gs, None, None, None, None, None, None
+        return gu, gk, gs, None, None, None, None, None, None, None
+
+
+def _scheme_is_upwind(scheme: str) -> bool:
+    if scheme not in ("central", "upwind"):
+        raise ValueError("scheme must be 'central' or 'upwind', got %r" % (scheme,))
+    return scheme == "upwind"
 
 
 def rollout(u0: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
-            last_only: bool = False, batch_chunk: int = 0, keep_features=None) -> torch.Tensor:
+            last_only: bool = False, batch_chunk: int = 0, keep_features=None, scheme: str = "central") -> torch.Tensor:
     """Fused forward-Euler rollout ``u <- u + dt*SymNet(FD2d(u))`` (rows a5-a10), differentiable
     w.r.t. ``u0``, the scaled ``kernels`` [N,k,k] and the flat ``symnet`` [C,Psym] (row a11).
 
@@ -237,17 +263,21 @@ def rollout(u0: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: in
     (as the reference's autograd does), False recomputes them there, None decides by
     ``FEATURE_CACHE_BYTES``.  The results are identical bit for bit.
 
+    ``scheme='upwind'``: the pseudo-upwind scheme (row f-1; ``include/pdenet_b200.h``): per output
+    channel and grid point the first-order inputs of the SymNet come from the filter as given or from
+    its flipped twin, by the sign of the SymNet's own derivative w.r.t. that input.
+
     Returns the states after every step ``[steps,B,C,H,W]`` (or only the last one)."""
     if steps < 1:
         raise ValueError("steps must be >= 1")
     return _Rollout.apply(u0, kernels, symnet, int(L), float(dt), int(steps), bool(last_only), int(batch_chunk),
-                          keep_features)
+                          keep_features, _scheme_is_upwind(scheme))
 
 
 # ------------------------------------------------------------------------------ row a8
 class _Rhs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, kernels, symnet, L, batch_chunk):
+    def forward(ctx, u, kernels, symnet, L, batch_chunk, upwind=False):
         u = _req(u, "u")
         kernels = _req(kernels, "kernels", u.dtype)
         symnet = _req(symnet, "symnet", u.dtype)
@@ -257,36 +287,41 @@ class _Rhs(torch.autograd.Function):
             raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
         out = torch.empty_like(u)
-        _lib.check(_lib.fn("pdenet_rhs_fwd", u.dtype)(_ptr(u), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, H, W, k,
-                                                      N, L, _stream()), "pdenet_rhs_fwd")
+        name = "pdenet_rhs_upwind_fwd" if upwind else "pdenet_rhs_fwd"
+        _lib.check(_lib.fn(name, u.dtype)(_ptr(u), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, H, W, k, N, L,
+                                          _stream()), name)
         ctx.save_for_backward(u, kernels, symnet)
-        ctx.cfg = (L, batch_chunk)
+        ctx.cfg = (L, batch_chunk, bool(upwind))
         return out
 
     @staticmethod
     def backward(ctx, grad):
         u, kernels, symnet = ctx.saved_tensors
-        L, batch_chunk = ctx.cfg
+        L, batch_chunk, upwind = ctx.cfg
         B, Cc, H, W = u.shape
         N, k, _ = kernels.shape
         grad = _req(grad, "grad_out", u.dtype)
-        nbytes = _lib.lib().pdenet_rollout_bwd_workspace_bytes(u.element_size(), B, Cc, H, W, k, N, L, batch_chunk)
+        wsfn = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes if upwind \
+            else _lib.lib().pdenet_rollout_bwd_workspace_bytes
+        nbytes = wsfn(u.element_size(), B, Cc, H, W, k, N, L, batch_chunk)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=u.device)
         need_u, need_k, need_s = ctx.needs_input_grad[:3]
         gu = torch.empty_like(u) if need_u else None
         gk = torch.empty_like(kernels) if need_k else None
         gs = torch.empty_like(symnet) if need_s else None
-        _lib.check(_lib.fn("pdenet_rhs_bwd", u.dtype)(
+        name = "pdenet_rhs_upwind_bwd" if upwind else "pdenet_rhs_bwd"
+        _lib.check(_lib.fn(name, u.dtype)(
             _ptr(u), _ptr(grad), _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs), _ptr(ws), nbytes,
-            batch_chunk, B, Cc, H, W, k, N, L, _stream()), "pdenet_rhs_bwd")
-        return gu, gk, gs, None, None
+            batch_chunk, B, Cc, H, W, k, N, L, _stream()), name)
+        return gu, gk, gs, None, None, None
 
 
-def rhs(u: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, batch_chunk: int = 0) -> torch.Tensor:
+def rhs(u: torch.Tensor, kernels: torch.Tensor, symnet: torch.Tensor, L: int, batch_chunk: int = 0,
+        scheme: str = "central") -> torch.Tensor:
     """The right-hand side ``F(u) = SymNet(FD2d(u))`` [B,C,H,W] itself (row a8, upstream
     ``POLYPDE2D.RightHandItems``): the fused step kernel without the Euler update, differentiable
-    w.r.t. ``u``, the scaled ``kernels`` and the flat ``symnet``."""
-    return _Rhs.apply(u, kernels, symnet, int(L), int(batch_chunk))
+    w.r.t. ``u``, the scaled ``kernels`` and the flat ``symnet``; ``scheme`` as in :func:`rollout`."""
+    return _Rhs.apply(u, kernels, symnet, int(L), int(batch_chunk), _scheme_is_upwind(scheme))
 
 
 # ------------------------------------------------------------------------------ row a12

@@ -272,3 +272,82 @@ def test_property_torch_and_numpy_oracles_agree(k, C, L, H, W, steps, seed):
     states, gu = out[0], out[1]
     assert np.allclose(states[-1], last.detach().numpy(), rtol=1e-11, atol=1e-12)
     assert np.allclose(gu, uc.grad.numpy(), rtol=1e-9, atol=1e-11)
+
+
+# ---- row f-1: pseudo-upwind scheme (restated from the paper's description; parity unpinned) ---------------
+def _asym_model(k=5, C=2, L=2, dx=0.3, seed=0, noise=5e-2):
+    """Bank with visibly one-sided first-order filters (moment noise) and a Burgers-like SymNet + noise."""
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(2)
+    M = O.initial_moments(k, orders) + noise * torch.randn(len(orders), k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    sym = (O.burgers_symnet(0.05) if C == 2 else torch.zeros(C, O.symnet_param_count(C * 6, L), dtype=torch.float64))
+    sym = sym + 0.1 * torch.randn(C, O.symnet_param_count(C * 6, L), generator=g, dtype=torch.float64)
+    return Ks, sym
+
+
+def test_upwind_twins_and_centred_filters():
+    """A centred first-derivative filter is its own twin, so on one-hot moments the upwind scheme IS the central
+    scheme; the twin of a one-sided filter is the same derivative with the opposite bias."""
+    orders = O.order_list(2)
+    Ks = O.scaled_kernels(O.initial_moments(5, orders), O.filter_scales(orders, 0.1))
+    tw = O.upwind_twins(Ks)
+    assert torch.allclose(tw[0], Ks[1], atol=1e-12) and torch.allclose(tw[1], Ks[2], atol=1e-12)
+    _, sym = _asym_model()
+    u = torch.randn(2, 2, 12, 14, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    assert torch.allclose(O.upwind_right_hand_items(u, Ks, sym, 2), O.right_hand_items(u, Ks, sym, 2), atol=1e-10)
+    # backward difference (uses x-1, x) <-> forward difference (uses x, x+1): both approximate d/dx
+    bwd = torch.zeros(3, 3, dtype=torch.float64)
+    bwd[1, 0], bwd[1, 1] = -1.0, 1.0
+    bank = torch.stack([torch.zeros(3, 3, dtype=torch.float64), bwd, bwd.t()])
+    tw = O.upwind_twins(bank)
+    fwd = torch.zeros(3, 3, dtype=torch.float64)
+    fwd[1, 1], fwd[1, 2] = -1.0, 1.0
+    assert torch.equal(tw[0], fwd) and torch.equal(tw[1], fwd.t())
+
+
+def test_upwind_selects_by_sign_of_velocity():
+    """Scalar advection u_t = a u_x with a constant-sign coefficient: the SymNet is linear, its derivative
+    w.r.t. u_x is `a` everywhere, so a >= 0 uses the filter as given and a < 0 its twin -- at every point."""
+    H = W = 16
+    dx = 2 * math.pi / W
+    bwd = torch.zeros(3, 3, dtype=torch.float64)
+    bwd[1, 0], bwd[1, 1] = -1.0 / dx, 1.0 / dx          # one-sided: (u(x) - u(x-dx)) / dx
+    ident = torch.zeros(3, 3, dtype=torch.float64)
+    ident[1, 1] = 1.0
+    Ks = torch.stack([ident, bwd, bwd.t()])             # max_order 1 bank: (0,0), (0,1), (1,0)
+    u = torch.sin(torch.arange(W, dtype=torch.float64) * dx)[None, None, None, :].expand(1, 1, H, W).contiguous()
+    for a in (0.7, -0.7):
+        sym = torch.zeros(1, O.symnet_param_count(3, 0), dtype=torch.float64)
+        sym[0, 1] = a                                   # out = a * u_x
+        F = O.upwind_right_hand_items(u, Ks, sym, 0)
+        ux_bwd = (u - torch.roll(u, 1, 3)) / dx
+        ux_fwd = (torch.roll(u, -1, 3) - u) / dx
+        assert torch.allclose(F, a * (ux_bwd if a >= 0 else ux_fwd), atol=1e-13)
+
+
+@pytest.mark.parametrize("k,C,L", [(5, 2, 2), (3, 1, 1), (7, 2, 2), (5, 1, 3)])
+def test_upwind_torch_oracle_matches_numpy_adjoint(k, C, L):
+    """The torch restatement (autograd through the detached selection) and the independent numpy restatement
+    (closed-form velocity, hand-derived adjoint, twins folded back) agree on states and every gradient."""
+    g = torch.Generator().manual_seed(3 + k)
+    orders = O.order_list(2)
+    M = O.initial_moments(k, orders) + 5e-2 * torch.randn(len(orders), k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, 0.3))
+    sym = 0.3 * torch.randn(C, O.symnet_param_count(C * 6, L), generator=g, dtype=torch.float64)
+    u0 = torch.randn(2, C, 9, 11, generator=g, dtype=torch.float64)
+    w = torch.randn(2, C, 9, 11, generator=g, dtype=torch.float64)
+    steps, dt = 2, 1e-2
+    lv = [t.clone().requires_grad_(True) for t in (u0, Ks, sym)]
+    out = O.upwind_rollout(*lv, L, dt, steps)[-1]
+    (out * w).sum().backward()
+    st, lam, dKs, dsym = ONP.upwind_rollout_fwd_bwd(u0.numpy(), Ks.numpy(), sym.numpy(), L, dt, steps, w.numpy())
+
+    def rel(a, b):
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    assert rel(out.detach().numpy(), st[-1]) < 1e-13
+    assert rel(lv[0].grad.numpy(), lam) < 1e-12
+    assert rel(lv[1].grad.numpy(), dKs) < 1e-12
+    assert rel(lv[2].grad.numpy(), dsym) < 1e-12
+    # and the scheme really differs from the central one for these one-sided filters
+    assert (out.detach() - O.rollout(u0, Ks, sym, L, dt, steps)[-1]).abs().max() > 1e-6

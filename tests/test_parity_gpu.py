@@ -449,6 +449,116 @@ def test_m2k_k2m_modules(P, cuda_device, k):
     assert rel(Md.grad, Mc.grad) < 1e-11
 
 
+# ------------------------------------------------------------------ row f-1: pseudo-upwind scheme
+UPWIND_CASES = [
+    # k, max_order, C, L, B, H, W, steps, dx, dt
+    (7, 2, 2, 2, 2, 40, 70, 3, 0.3, 1e-2),      # the headline bank (N=6, C=2, L=2: compile-time depth path)
+    (5, 2, 2, 2, 3, 37, 53, 2, 0.2, 1e-2),      # ragged tiles
+    (5, 2, 1, 3, 2, 20, 70, 2, 0.3, 1e-2),      # one channel, run-time depth
+    (3, 1, 1, 1, 2, 8, 9, 3, 0.5, 1e-2),        # max_order 1 bank (3 filters), tiny grid wrapping several times
+    (5, 1, 2, 0, 2, 33, 31, 2, 0.3, 1e-2),      # L = 0: linear SymNet, the velocity is a weight
+    (7, 2, 2, 4, 1, 24, 40, 2, 0.3, 1e-2),      # deeper SymNet (32-long gradient vectors)
+    (7, 2, 2, 2, 1, 2, 3, 2, 0.5, 1e-2),        # grid smaller than the stencil
+]
+
+
+def upwind_both(P, dev, case, dtype, grad_all, batch_chunk=0, noise=5e-2):
+    k, max_order, C, L, B, H, W, steps, dx, dt = case
+    g = torch.Generator().manual_seed(17)
+    orders = O.order_list(max_order)
+    N = len(orders)
+    # visibly one-sided filters: without moment noise the twins coincide with the central filters
+    M = O.initial_moments(k, orders) + noise * torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    sym = 0.3 * torch.randn(C, O.symnet_param_count(C * N, L), generator=g, dtype=torch.float64)
+    u0 = smooth_field(B, C, H, W, 18)
+    w = torch.randn(steps, B, C, H, W, generator=g, dtype=torch.float64)
+    if not grad_all:
+        w[:-1] = 0
+    uc, Kc, sc = u0.clone().requires_grad_(True), Ks.clone().requires_grad_(True), sym.clone().requires_grad_(True)
+    ref = torch.stack(O.upwind_rollout(uc, Kc, sc, L, dt, steps))
+    (ref * w).sum().backward()
+    central = torch.stack(O.rollout(u0, Ks, sym, L, dt, steps))
+    ud, Kd, sd = [t.to(dev, dtype).requires_grad_(True) for t in (u0, Ks, sym)]
+    if grad_all:
+        st = P.rollout(ud, Kd, sd, L, dt, steps, batch_chunk=batch_chunk, scheme="upwind")
+        (st * w.to(dev, dtype)).sum().backward()
+    else:
+        st = P.rollout(ud, Kd, sd, L, dt, steps, last_only=True, batch_chunk=batch_chunk, scheme="upwind")[None]
+        (st[0] * w[-1].to(dev, dtype)).sum().backward()
+        ref, central = ref[-1:], central[-1:]
+    return (st, ud.grad, Kd.grad, sd.grad), (ref, uc.grad, Kc.grad, sc.grad), central
+
+
+@pytest.mark.parametrize("case", UPWIND_CASES)
+@pytest.mark.parametrize("grad_all", [False, True])
+def test_upwind_rollout_parity_fp64(P, cuda_device, case, grad_all):
+    """scheme='upwind' through the fused kernels (twins from the staged tile, per-point select, reverse with the
+    selection held constant, twin gradients folded back) against the oracle restatement."""
+    got, ref, central = upwind_both(P, cuda_device, case, torch.float64, grad_all, batch_chunk=2 if grad_all else 0)
+    steps = case[7]
+    for n, a, b in zip(["states", "grad_u0", "grad_kernels", "grad_symnet"], got, ref):
+        assert rel(a, b) < TOL[torch.float64] * steps, (n, rel(a, b))
+    assert rel(central, ref[0]) > 1e-7      # the case really exercises the selection
+
+
+def test_upwind_rollout_fp32(P, cuda_device):
+    """fp32: a point whose velocity is within rounding of zero may select the other twin than the fp64 oracle;
+    the velocity is ~0 there, so the effect on F is second order -- states within 1e-5 per step."""
+    case = UPWIND_CASES[0]
+    got, ref, _ = upwind_both(P, cuda_device, case, torch.float32, True)
+    assert rel(got[0], ref[0]) < TOL[torch.float32] * case[7]
+
+
+def test_upwind_module_and_rhs(P, cuda_device):
+    """POLYPDE2D(scheme='upwind'): forward / RightHandItems / gradients on the moments and the nn.Linear
+    parameters against the oracle; with centred (one-hot) filters it equals the central scheme."""
+    dev = cuda_device
+    dt, dx, k, L = 1e-2, 0.25, 5, 2
+    model = P.POLYPDE2D(dt, dx, k, 2, "moment", "u,v", hidden_layers=L, scheme="upwind").to(dev)
+    central = P.POLYPDE2D(dt, dx, k, 2, "moment", "u,v", hidden_layers=L, scheme="central").to(dev)
+    g = torch.Generator().manual_seed(31)
+    u0 = smooth_field(2, 2, 30, 34, 32)
+    with torch.no_grad():
+        for p, q in zip(model.expr_params(), central.expr_params()):
+            p.copy_((0.3 * torch.randn(p.shape, generator=g, dtype=torch.float64)).to(dev))
+            q.copy_(p)
+        assert torch.allclose(model(u0.to(dev), 2 * dt), central(u0.to(dev), 2 * dt), atol=1e-12)
+        for fd in model.fds:
+            fd.moment.add_((5e-2 * torch.randn(k, k, generator=g, dtype=torch.float64)).to(dev))
+        model.diff_x_proj()
+    orders = O.order_list(2)
+    M = torch.stack([fd.moment.detach().cpu() for fd in model.fds]).requires_grad_(True)
+    sym = torch.stack([pl.flat_params().detach().cpu() for pl in model.polys]).requires_grad_(True)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    w = torch.randn(u0.shape, generator=g, dtype=torch.float64)
+    # RightHandItems
+    F_ref = O.upwind_right_hand_items(u0, Ks.detach(), sym.detach(), L)
+    assert rel(model.RightHandItems(u0.to(dev)), F_ref) < 1e-11
+    # forward(T) + gradients
+    out = model(u0.to(dev), 3 * dt)
+    (out * w.to(dev)).sum().backward()
+    model.diff_grad_proj()
+    ref = O.upwind_rollout(u0, Ks, sym, L, dt, 3)[-1]
+    (ref * w).sum().backward()
+    assert rel(out, ref) < 3e-10
+    mask = torch.stack([O.pinned_mask(k, o, "moment") for o in orders])
+    gm = torch.stack([fd.moment.grad.cpu() for fd in model.fds])
+    assert rel(gm, M.grad.masked_fill(mask, 0)) < 3e-10
+    gs = torch.stack([torch.cat([q.grad.reshape(-1).cpu() for q in pl.parameters()]) for pl in model.polys])
+    assert rel(gs, sym.grad) < 3e-10
+    # refused, not mis-computed: banks the scheme is not compiled for
+    from pdenet_b200 import _lib
+    assert _lib.lib().pdenet_upwind_supported(8, 7, 6, 2, 2) == 1
+    assert _lib.lib().pdenet_upwind_supported(8, 7, 6, 3, 2) == 0
+    with pytest.raises(_lib.PdenetError) as e:
+        P.rollout(torch.zeros(1, 3, 8, 8, dtype=torch.float64, device=dev),
+                  torch.zeros(6, 5, 5, dtype=torch.float64, device=dev),
+                  torch.zeros(3, P.symnet_param_count(18, 1), dtype=torch.float64, device=dev), 1, 1e-2, 1,
+                  scheme="upwind")
+    assert e.value.code == _lib.E_UNSUPPORTED
+
+
 def test_shift_equivariance_large(P, cuda_device):
     """Size-independent property at a size the oracle is too slow for (KAT-5 on the CUDA path)."""
     k, max_order, C, L, dx, dt = 7, 2, 2, 2, 2 * math.pi / 512, 1e-3
