@@ -376,9 +376,8 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
 }
 
 // Filter gradient: warps own filters; N filters are covered by launches of nw in {6, 3, 2, 1}
-// filters each (nw divides the 6 warps of a CTA; the other warps split the tile rows).
-constexpr int kFGradWarps = 6;
-constexpr int kFGradCtasPerSm = 2;
+// filters each (nw divides the warps of a CTA; the other warps split the tile rows).  Geometry
+// (kFGradWarps, kFGradCtasPerSm): params.cuh.
 static int dk_slot_count(int sms) { return sms * kFGradCtasPerSm * kFGradWarps; }
 
 template <typename T, int K>
@@ -402,7 +401,9 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
   int n0 = 0;
   while (n0 < N) {
     const int left = N - n0;
-    const int nw = left >= 6 ? 6 : (left >= 3 ? 3 : (left >= 2 ? 2 : 1));
+    int nw = 1; // largest divisor of the CTA's warp count that does not exceed the filters left
+    for (int d = 1; d <= kFGradWarps; ++d)
+      if (kFGradWarps % d == 0 && d <= left) nw = d;
     p.n0 = n0;
     p.nw = nw;
     ProfScope ps(3, st);

@@ -79,6 +79,17 @@ template <typename T> struct AdjParams {
   int tiles_x, tiles_y, n_items;
 };
 
+// Filter-gradient kernel (B2) geometry.  Warps of a CTA own (filter, row part) pairs.  12 warps in ONE
+// CTA per SM put exactly 3 warps on each of the 4 SM sub-partitions; the first version ran 2 CTAs of 6
+// warps, which lands 4 / 4 / 2 / 2 warps on the sub-partitions (warp w of a CTA goes to sub-partition
+// w mod 4): the two busy ones bound the kernel at 75 % while the others wait at the item barrier (ncu:
+// barrier stall 1.04 per issued instruction).
+#ifndef PDENET_B2_WARPS
+#define PDENET_B2_WARPS 12
+#endif
+constexpr int kFGradWarps = PDENET_B2_WARPS;
+constexpr int kFGradCtasPerSm = kFGradWarps <= 6 ? 2 : 1;
+
 template <typename T> struct FGradParams {
   const T *g; // [B][C*N][g_rows][W]
   int g_rows, g_off;
