@@ -10,6 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpdenet_b200.so")
+TORCH_LIB_PATH = os.path.join(_HERE, "libpdenet_b200_torch.so")
 
 OK, E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_CUDA = 0, -1, -2, -3, -4
 GRAD_LAST, GRAD_ALL = 0, 1
@@ -121,6 +122,38 @@ def lib() -> C.CDLL:
                 fn.restype, fn.argtypes = res, args
         _lib = l
     return _lib
+
+
+_torch_ops = False   # False = not tried yet; None = ctypes binding selected / shim unavailable
+
+
+def torch_ops():
+    """``torch.ops.pdenet_b200`` -- the hot-path entries registered as dispatcher ops by the TORCH_LIBRARY shim
+    (csrc/torch_shim.cpp -> libpdenet_b200_torch.so, a torch C++ extension over the same C-ABI) -- or None when
+    ``PDENET_BINDING=ctypes`` selects the plain ctypes binding (option B).  Both bindings call
+    the same ``extern "C"`` entries of libpdenet_b200.so."""
+    global _torch_ops
+    if _torch_ops is False:
+        _torch_ops = None
+        if os.environ.get("PDENET_BINDING", "torch").lower() != "ctypes":
+            lib()   # builds / verifies both shared objects
+            import torch
+            torch.ops.load_library(TORCH_LIB_PATH)
+            _torch_ops = torch.ops.pdenet_b200
+    return _torch_ops
+
+
+def call_op(what: str, fn, *args):
+    """Call a dispatcher op of the shim; a C-ABI error code comes back as the same :class:`PdenetError` the
+    ctypes binding raises."""
+    try:
+        return fn(*args)
+    except RuntimeError as e:
+        import re
+        m = re.search(r"\(code (-?\d+)\)", str(e))
+        if m:
+            raise PdenetError(int(m.group(1)), what) from None
+        raise
 
 
 class PdenetError(RuntimeError):

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpdenet_b200.so")
+TORCH_LIB = os.path.join(HERE, "libpdenet_b200_torch.so")   # TORCH_LIBRARY shim over the C-ABI (csrc/torch_shim.cpp)
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -25,7 +26,7 @@ KS = [3, 5, 7]
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".cpp"))] + [
         os.path.join(HERE, "..", "include", "pdenet_b200.h")]
 
 
@@ -49,9 +50,34 @@ def source_hash() -> str:
 def up_to_date() -> bool:
     """True if the shared object exists and was built from the present sources (content hash, not
     mtimes: the tree is copied to the GPU box without them)."""
-    if not os.path.exists(LIB) or not os.path.exists(ID_FILE):
+    if not os.path.exists(LIB) or not os.path.exists(TORCH_LIB) or not os.path.exists(ID_FILE):
         return False
     return open(ID_FILE).read().strip() == source_hash()
+
+
+def _torch_paths():
+    import torch
+    from torch.utils import cpp_extension as ce
+    inc = ce.include_paths()
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True))
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    return inc + [cuda_inc], libdir, abi
+
+
+def _torch_shim_compile_cmd(obj):
+    """g++ (no device code in the shim): torch headers + the C-ABI header."""
+    inc, _, abi = _torch_paths()
+    cxx = os.environ.get("CXX", "g++")
+    return [cxx, "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi,
+            *["-isystem" + i for i in inc], "-c", os.path.join(CSRC, "torch_shim.cpp"), "-o", obj]
+
+
+def _torch_shim_link_cmd(obj):
+    _, libdir, _ = _torch_paths()
+    cxx = os.environ.get("CXX", "g++")
+    return [cxx, "-shared", "-o", TORCH_LIB, obj, "-L" + libdir, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
+            "-ltorch", "-L" + HERE, "-l:libpdenet_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + libdir]
 
 
 def _run(cmd):
@@ -76,11 +102,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     o = os.path.join(OBJ, "api.o")
     jobs.append((o, [nvcc, *NVCC_FLAGS, '-DPDENET_BUILD_ID="%s"' % build_id, "-c", os.path.join(CSRC, "api.cu"),
                      "-o", o]))
-    with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-        for out in ex.map(lambda j: _run(j[1]), jobs):
+    shim_obj = os.path.join(OBJ, "torch_shim.o")
+    shim_job = (shim_obj, _torch_shim_compile_cmd(shim_obj))
+    with cf.ThreadPoolExecutor(max_workers=min(len(jobs) + 1, os.cpu_count() or 4)) as ex:
+        for out in ex.map(lambda j: _run(j[1]), jobs + [shim_job]):
             if verbose and out.strip():
                 print(out)
     _run([nvcc, "-shared", "-o", LIB, *[j[0] for j in jobs], "-gencode", "arch=compute_100a,code=sm_100a"])
+    _run(_torch_shim_link_cmd(shim_obj))
     with open(ID_FILE, "w") as f:
         f.write(build_id + "\n")
     return LIB

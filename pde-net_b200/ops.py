@@ -49,16 +49,24 @@ class _M2K(torch.autograd.Function):
     def forward(ctx, moments, scale, mask):
         moments = _req(moments, "moments")
         N, k, _ = moments.shape
+        ctx.scale, ctx.mask = scale, mask
+        T = _lib.torch_ops()
+        if T is not None:
+            _scale_array(scale, N)   # length check
+            return _lib.call_op("pdenet_m2k", T.m2k, moments, [] if scale is None else [float(s) for s in scale], None)
         out = torch.empty_like(moments)
         _lib.check(_lib.fn("pdenet_m2k", moments.dtype)(_ptr(moments), _scale_array(scale, N), _ptr(out), N, k,
                                                         _stream()), "pdenet_m2k")
-        ctx.scale, ctx.mask = scale, mask
         return out
 
     @staticmethod
     def backward(ctx, gk):
         gk = _req(gk, "grad_kernels")
         N, k, _ = gk.shape
+        T = _lib.torch_ops()
+        if T is not None:
+            sc = [] if ctx.scale is None else [float(s) for s in ctx.scale]
+            return _lib.call_op("pdenet_m2k_bwd", T.m2k_bwd, gk, sc, ctx.mask), None, None
         gm = torch.empty_like(gk)
         _lib.check(_lib.fn("pdenet_m2k_bwd", gk.dtype)(_ptr(gk), _scale_array(ctx.scale, N), _ptr(ctx.mask),
                                                        _ptr(gm), N, k, _stream()), "pdenet_m2k_bwd")
@@ -153,6 +161,78 @@ def symnet_eval(feat: torch.Tensor, flat: torch.Tensor, L: int) -> torch.Tensor:
 FEATURE_CACHE_BYTES = int(float(os.environ.get("PDENET_FEATURE_CACHE_GB", "32")) * 2 ** 30)
 
 
+_F_KEEP, _F_UPWIND, _F_LAST = 1, 2, 4   # flags of the dispatcher ops (csrc/torch_shim.cpp)
+
+
+def _rollout_fwd_ctypes(u0, kernels, symnet, L, dt, steps, keep, upwind):
+    B, Cc, H, W = u0.shape
+    N, k, _ = kernels.shape
+    states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
+    feats = None
+    if upwind:
+        _lib.check(_lib.fn("pdenet_rollout_fwd_upwind", u0.dtype)(
+            _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
+            _stream()), "pdenet_rollout_fwd_upwind")
+    elif keep:
+        feats = torch.empty(steps, B, Cc * N, H, W, dtype=u0.dtype, device=u0.device)
+        _lib.check(_lib.fn("pdenet_rollout_fwd_keep", u0.dtype)(
+            _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), _ptr(feats), B, Cc, H, W, k, N, L, steps,
+            float(dt), _stream()), "pdenet_rollout_fwd_keep")
+    else:
+        _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
+            _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
+            _stream()), "pdenet_rollout_fwd")
+    return states, feats
+
+
+def _rollout_fwd(u0, kernels, symnet, L, dt, steps, keep, upwind):
+    """-> (states, feats or None) through the dispatcher op (TORCH_LIBRARY shim) or the ctypes binding."""
+    T = _lib.torch_ops()
+    if T is None:
+        return _rollout_fwd_ctypes(u0, kernels, symnet, L, dt, steps, keep, upwind)
+    flags = (_F_KEEP if keep and not upwind else 0) | (_F_UPWIND if upwind else 0)
+    states, feats = _lib.call_op("pdenet_rollout_fwd", T.rollout_fwd, u0, kernels, symnet, L, float(dt), steps, flags)
+    return states, (feats if flags & _F_KEEP else None)
+
+
+def _rollout_bwd(u0, states, feats, grad, kernels, symnet, L, dt, steps, last_only, batch_chunk, need, upwind):
+    B, Cc, H, W = u0.shape
+    N, k, _ = kernels.shape
+    need_u, need_k, need_s = need
+    T = _lib.torch_ops()
+    if T is not None:
+        flags = (_F_KEEP if feats is not None else 0) | (_F_UPWIND if upwind else 0) | (_F_LAST if last_only else 0)
+        empty = u0.new_empty(0)
+        gu, gk, gs = _lib.call_op("pdenet_rollout_bwd", T.rollout_bwd, u0, states if states is not None else empty,
+                                  feats if feats is not None else empty, grad, kernels, symnet, L, float(dt), steps,
+                                  batch_chunk, bool(need_u), bool(need_k), bool(need_s), flags)
+        return (gu if need_u else None), (gk if need_k else None), (gs if need_s else None)
+    es = u0.element_size()
+    wsfn = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes if upwind \
+        else _lib.lib().pdenet_rollout_bwd_workspace_bytes
+    nbytes = wsfn(es, B, Cc, H, W, k, N, L, batch_chunk)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
+    gu = torch.empty_like(u0) if need_u else None
+    gk = torch.empty_like(kernels) if need_k else None
+    gs = torch.empty_like(symnet) if need_s else None
+    mode = _lib.GRAD_LAST if last_only else _lib.GRAD_ALL
+    if upwind:
+        _lib.check(_lib.fn("pdenet_rollout_bwd_upwind", u0.dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
+            _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
+            "pdenet_rollout_bwd_upwind")
+    elif feats is not None:
+        _lib.check(_lib.fn("pdenet_rollout_bwd_kept", u0.dtype)(
+            _ptr(u0), _ptr(states), _ptr(feats), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu),
+            _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
+            "pdenet_rollout_bwd_kept")
+    else:
+        _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
+            _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()), "pdenet_rollout_bwd")
+    return gu, gk, gs
+
+
 class _Rollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u0, kernels, symnet, L, dt, steps, last_only, batch_chunk, keep_features, upwind=False):
@@ -164,44 +244,26 @@ class _Rollout(torch.autograd.Function):
         if tuple(symnet.shape) != (Cc, symnet_param_count(Cc * N, L)):
             raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
-        states = torch.empty(steps, B, Cc, H, W, dtype=u0.dtype, device=u0.device)
         ctx.upwind = bool(upwind)
+        auto = False
         if upwind:   # pseudo-upwind scheme (row f-1): features are always recomputed by the reverse pass
-            _lib.check(_lib.fn("pdenet_rollout_fwd_upwind", u0.dtype)(
-                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
-                _stream()), "pdenet_rollout_fwd_upwind")
-            ctx.feats = None
-            ctx.cfg = (L, float(dt), steps, last_only, batch_chunk)
-            if last_only:
-                ctx.save_for_backward(u0, kernels, symnet)
-                ctx.states = states
-                return states[-1]
-            ctx.save_for_backward(u0, kernels, symnet, states)
-            return states
-        feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
-        auto = keep_features is None
-        if auto:
-            # a few banks (3 channels, deep SymNet, fp64) only fit the reverse pass with kept features
-            needs = _lib.lib().pdenet_rollout_bwd_needs_features(u0.element_size(), k, N, Cc, L) == 1
-            keep_features = needs or feat_bytes <= FEATURE_CACHE_BYTES
-            auto = not needs
-        keep_features = bool(keep_features) and any(ctx.needs_input_grad[:3])
-        feats = None
-        if keep_features:
-            try:
-                feats = torch.empty(steps, B, Cc * N, H, W, dtype=u0.dtype, device=u0.device)
-            except torch.OutOfMemoryError:
-                if not auto:
-                    raise
-                keep_features = False  # no room: the reverse pass recomputes the features instead
-        if keep_features:
-            _lib.check(_lib.fn("pdenet_rollout_fwd_keep", u0.dtype)(
-                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), _ptr(feats), B, Cc, H, W, k, N, L, steps,
-                float(dt), _stream()), "pdenet_rollout_fwd_keep")
+            keep_features = False
         else:
-            _lib.check(_lib.fn("pdenet_rollout_fwd", u0.dtype)(
-                _ptr(u0), _ptr(kernels), _ptr(symnet), _ptr(states), B, Cc, H, W, k, N, L, steps, float(dt),
-                _stream()), "pdenet_rollout_fwd")
+            feat_bytes = steps * B * Cc * N * H * W * u0.element_size()
+            auto = keep_features is None
+            if auto:
+                # a few banks (3 channels, deep SymNet, fp64) only fit the reverse pass with kept features
+                needs = _lib.lib().pdenet_rollout_bwd_needs_features(u0.element_size(), k, N, Cc, L) == 1
+                keep_features = needs or feat_bytes <= FEATURE_CACHE_BYTES
+                auto = not needs
+            keep_features = bool(keep_features) and any(ctx.needs_input_grad[:3])
+        try:
+            states, feats = _rollout_fwd(u0, kernels, symnet, L, dt, steps, keep_features, ctx.upwind)
+        except torch.OutOfMemoryError:
+            if not (auto and keep_features):
+                raise
+            # no room for the feature buffer: the reverse pass recomputes the features instead
+            states, feats = _rollout_fwd(u0, kernels, symnet, L, dt, steps, False, False)
         ctx.feats = feats  # an intermediate, never an output: no reference cycle
         ctx.cfg = (L, float(dt), steps, last_only, batch_chunk)
         if last_only:  # `states` is an intermediate: keep it on ctx (no cycle, it is not an output)
@@ -218,33 +280,9 @@ class _Rollout(torch.autograd.Function):
         else:
             u0, kernels, symnet, states = ctx.saved_tensors
         L, dt, steps, last_only, batch_chunk = ctx.cfg
-        B, Cc, H, W = u0.shape
-        N, k, _ = kernels.shape
         grad = _req(grad, "grad_states", u0.dtype)
-        es = u0.element_size()
-        wsfn = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes if ctx.upwind \
-            else _lib.lib().pdenet_rollout_bwd_workspace_bytes
-        nbytes = wsfn(es, B, Cc, H, W, k, N, L, batch_chunk)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
-        need_u, need_k, need_s = ctx.needs_input_grad[:3]
-        gu = torch.empty_like(u0) if need_u else None
-        gk = torch.empty_like(kernels) if need_k else None
-        gs = torch.empty_like(symnet) if need_s else None
-        mode = _lib.GRAD_LAST if last_only else _lib.GRAD_ALL
-        if ctx.upwind:
-            _lib.check(_lib.fn("pdenet_rollout_bwd_upwind", u0.dtype)(
-                _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
-                _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
-                "pdenet_rollout_bwd_upwind")
-        elif ctx.feats is not None:
-            _lib.check(_lib.fn("pdenet_rollout_bwd_kept", u0.dtype)(
-                _ptr(u0), _ptr(states), _ptr(ctx.feats), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu),
-                _ptr(gk), _ptr(gs), _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()),
-                "pdenet_rollout_bwd_kept")
-        else:
-            _lib.check(_lib.fn("pdenet_rollout_bwd", u0.dtype)(
-                _ptr(u0), _ptr(states), _ptr(grad), mode, _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs),
-                _ptr(ws), nbytes, batch_chunk, B, Cc, H, W, k, N, L, steps, dt, _stream()), "pdenet_rollout_bwd")
+        gu, gk, gs = _rollout_bwd(u0, states, ctx.feats, grad, kernels, symnet, L, dt, steps, last_only, batch_chunk,
+                                  ctx.needs_input_grad[:3], ctx.upwind)
         return gu, gk, gs, None, None, None, None, None, None, None
 
 
@@ -286,10 +324,14 @@ class _Rhs(torch.autograd.Function):
         if tuple(symnet.shape) != (Cc, symnet_param_count(Cc * N, L)):
             raise ValueError("symnet must be [C, Psym] = [%d, %d], got %s"
                              % (Cc, symnet_param_count(Cc * N, L), tuple(symnet.shape)))
-        out = torch.empty_like(u)
         name = "pdenet_rhs_upwind_fwd" if upwind else "pdenet_rhs_fwd"
-        _lib.check(_lib.fn(name, u.dtype)(_ptr(u), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, H, W, k, N, L,
-                                          _stream()), name)
+        T = _lib.torch_ops()
+        if T is not None:
+            out = _lib.call_op(name, T.rhs_fwd, u, kernels, symnet, L, _F_UPWIND if upwind else 0)
+        else:
+            out = torch.empty_like(u)
+            _lib.check(_lib.fn(name, u.dtype)(_ptr(u), _ptr(kernels), _ptr(symnet), _ptr(out), B, Cc, H, W, k, N, L,
+                                              _stream()), name)
         ctx.save_for_backward(u, kernels, symnet)
         ctx.cfg = (L, batch_chunk, bool(upwind))
         return out
@@ -301,6 +343,13 @@ class _Rhs(torch.autograd.Function):
         B, Cc, H, W = u.shape
         N, k, _ = kernels.shape
         grad = _req(grad, "grad_out", u.dtype)
+        name = "pdenet_rhs_upwind_bwd" if upwind else "pdenet_rhs_bwd"
+        T = _lib.torch_ops()
+        if T is not None:
+            nu, nk, ns = ctx.needs_input_grad[:3]
+            gu, gk, gs = _lib.call_op(name, T.rhs_bwd, u, grad, kernels, symnet, L, batch_chunk, bool(nu), bool(nk),
+                                      bool(ns), _F_UPWIND if upwind else 0)
+            return (gu if nu else None), (gk if nk else None), (gs if ns else None), None, None, None
         wsfn = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes if upwind \
             else _lib.lib().pdenet_rollout_bwd_workspace_bytes
         nbytes = wsfn(u.element_size(), B, Cc, H, W, k, N, L, batch_chunk)
@@ -309,7 +358,6 @@ class _Rhs(torch.autograd.Function):
         gu = torch.empty_like(u) if need_u else None
         gk = torch.empty_like(kernels) if need_k else None
         gs = torch.empty_like(symnet) if need_s else None
-        name = "pdenet_rhs_upwind_bwd" if upwind else "pdenet_rhs_bwd"
         _lib.check(_lib.fn(name, u.dtype)(
             _ptr(u), _ptr(grad), _ptr(kernels), _ptr(symnet), _ptr(gu), _ptr(gk), _ptr(gs), _ptr(ws), nbytes,
             batch_chunk, B, Cc, H, W, k, N, L, _stream()), name)
@@ -336,10 +384,15 @@ class _LinearRollout(torch.autograd.Function):
         N, k, _ = kernels.shape
         if tuple(coe.shape) != (N, H, W):
             raise ValueError("coe must be [N,H,W]")
-        states = torch.empty(steps, B, H, W, dtype=u0.dtype, device=u0.device)
-        _lib.check(_lib.fn("pdenet_linear_rollout_fwd", u0.dtype)(
-            _ptr(u0), _ptr(id_kernel), _ptr(kernels), _ptr(coe), _ptr(states), B, H, W, k, N, steps, float(dt),
-            _stream()), "pdenet_linear_rollout_fwd")
+        T = _lib.torch_ops()
+        if T is not None:
+            states = _lib.call_op("pdenet_linear_rollout_fwd", T.linear_rollout_fwd, u0, id_kernel, kernels, coe,
+                                  float(dt), steps)
+        else:
+            states = torch.empty(steps, B, H, W, dtype=u0.dtype, device=u0.device)
+            _lib.check(_lib.fn("pdenet_linear_rollout_fwd", u0.dtype)(
+                _ptr(u0), _ptr(id_kernel), _ptr(kernels), _ptr(coe), _ptr(states), B, H, W, k, N, steps, float(dt),
+                _stream()), "pdenet_linear_rollout_fwd")
         ctx.cfg = (float(dt), steps, last_only)
         if last_only:
             ctx.save_for_backward(u0, id_kernel, kernels, coe)
@@ -358,6 +411,12 @@ class _LinearRollout(torch.autograd.Function):
         B, H, W = u0.shape
         N, k, _ = kernels.shape
         grad = _req(grad, "grad_states", u0.dtype)
+        T = _lib.torch_ops()
+        if T is not None:
+            n = [bool(x) for x in ctx.needs_input_grad[:4]]
+            out = _lib.call_op("pdenet_linear_rollout_bwd", T.linear_rollout_bwd, u0, states, grad, id_kernel, kernels,
+                               coe, dt, steps, bool(last_only), *n)
+            return tuple(g if need else None for g, need in zip(out, n)) + (None, None, None)
         nbytes = _lib.lib().pdenet_linear_rollout_bwd_workspace_bytes(u0.element_size(), B, H, W, k, N)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
         need = ctx.needs_input_grad

@@ -198,3 +198,21 @@ def test_bench_model_equals_oracle_model(built):
     assert orders == o2 and torch.equal(M, M2) and torch.equal(sym, sym2)
     assert torch.equal(torch.tensor(scales, dtype=torch.float64), s2)
     assert bench.step_dt(dx) == dx * dx
+
+
+def test_torch_library_shim_registers_the_ops(built):
+    """The TORCH_LIBRARY shim (csrc/torch_shim.cpp -> libpdenet_b200_torch.so) loads next to the C-ABI library
+    and registers the hot-path entries as dispatcher ops (CUDA backend only: a CPU tensor has no kernel)."""
+    from pdenet_b200 import _lib
+    T = _lib.torch_ops()
+    assert T is not None and os.path.exists(_lib.TORCH_LIB_PATH)
+    for name in ("rollout_fwd", "rollout_bwd", "rhs_fwd", "rhs_bwd", "m2k", "m2k_bwd", "linear_rollout_fwd",
+                 "linear_rollout_bwd"):
+        assert hasattr(T, name), name
+    schema = str(T.rollout_fwd.default._schema)
+    assert "Tensor u0" in schema and "int steps" in schema
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        T.m2k(torch.zeros(1, 3, 3, dtype=torch.float64), [], None)       # no CPU kernel: there is no CPU fallback
+    # the shim links the C-ABI library instead of carrying kernels of its own
+    out = subprocess.run(["ldd", _lib.TORCH_LIB_PATH], capture_output=True, text=True).stdout
+    assert "libpdenet_b200.so" in out

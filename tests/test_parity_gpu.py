@@ -1062,6 +1062,28 @@ def test_concurrent_streams_use_separate_constant_slots(P, cuda_device):
             assert torch.equal(outs[i], ref[i]), (rep, i)
 
 
+def test_ctypes_and_dispatcher_bindings_agree(P, cuda_device):
+    """The two bindings of the C-ABI -- dispatcher ops of the TORCH_LIBRARY shim (default) and plain ctypes
+    (PDENET_BINDING=ctypes) -- reach the same entries: bit-identical states and gradients, same error type."""
+    from pdenet_b200 import _lib
+    case = CASES[2]
+    assert _lib.torch_ops() is not None
+    a, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=2, keep=True)
+    saved = _lib._torch_ops
+    try:
+        _lib._torch_ops = None          # what PDENET_BINDING=ctypes selects
+        b, _ = run_both(P, cuda_device, case, torch.float64, True, batch_chunk=2, keep=True)
+    finally:
+        _lib._torch_ops = saved
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    with pytest.raises(_lib.PdenetError) as e:   # an unsupported bank through the dispatcher op
+        P.rollout(torch.zeros(1, 2, 8, 8, dtype=torch.float64, device=cuda_device),
+                  torch.zeros(10, 5, 5, dtype=torch.float64, device=cuda_device),
+                  torch.zeros(2, P.symnet_param_count(20, 1), dtype=torch.float64, device=cuda_device), 1, 1e-2, 1)
+    assert e.value.code == _lib.E_UNSUPPORTED
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors(P, cuda_device):
     from pdenet_b200 import _lib
