@@ -65,17 +65,24 @@ def _torch_paths():
     return inc + [cuda_inc], libdir, abi
 
 
+def _host_cxx():
+    """The system g++ -- deliberately NOT $CXX: this image exports CXX=/opt/gcc/bin/g++, a wrapper whose search
+    path only has the static libstdc++.a, and a shim carrying its own copy of libstdc++ next to torch's shared
+    one crashes the first time it formats a number into an error message (two std::locale worlds)."""
+    return os.environ.get("PDENET_CXX", "g++")
+
+
 def _torch_shim_compile_cmd(obj):
     """g++ (no device code in the shim): torch headers + the C-ABI header."""
     inc, _, abi = _torch_paths()
-    cxx = os.environ.get("CXX", "g++")
+    cxx = _host_cxx()
     return [cxx, "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi,
             *["-isystem" + i for i in inc], "-c", os.path.join(CSRC, "torch_shim.cpp"), "-o", obj]
 
 
 def _torch_shim_link_cmd(obj):
     _, libdir, _ = _torch_paths()
-    cxx = os.environ.get("CXX", "g++")
+    cxx = _host_cxx()
     return [cxx, "-shared", "-o", TORCH_LIB, obj, "-L" + libdir, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
             "-ltorch", "-L" + HERE, "-l:libpdenet_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + libdir]
 
@@ -110,6 +117,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(out)
     _run([nvcc, "-shared", "-o", LIB, *[j[0] for j in jobs], "-gencode", "arch=compute_100a,code=sm_100a"])
     _run(_torch_shim_link_cmd(shim_obj))
+    syms = _run(["nm", "-D", "--defined-only", TORCH_LIB])
+    if "_ZNSo9_M_insertIlEERSoT_" in syms:
+        raise RuntimeError("libpdenet_b200_torch.so carries a static copy of libstdc++ (host compiler %s): it must "
+                           "link the shared one torch uses" % _host_cxx())
     with open(ID_FILE, "w") as f:
         f.write(build_id + "\n")
     return LIB
