@@ -111,8 +111,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
                      "-o", o]))
     shim_obj = os.path.join(OBJ, "torch_shim.o")
     shim_job = (shim_obj, _torch_shim_compile_cmd(shim_obj))
+
+    def compile_job(job):
+        """Compile one object unless an object built from the same inputs (sources it can include + command
+        line, content-hashed) is already there: an edit of api.cu does not recompile the six kernel units."""
+        import hashlib
+        obj, cmd = job
+        name = os.path.basename(obj)
+        if name.startswith("inst_"):
+            deps = [f for f in _sources() if f.endswith(".cuh") or f.endswith("inst.cu")]
+        elif name == "api.o":
+            deps = [f for f in _sources() if not f.endswith(".cpp") and not f.endswith("inst.cu")]
+        else:
+            deps = [f for f in _sources() if f.endswith((".cpp", ".h"))]
+        h = hashlib.sha256(" ".join(c for c in cmd if "PDENET_BUILD_ID" not in c).encode())
+        for f in deps:
+            h.update(open(f, "rb").read())
+        key = h.hexdigest()
+        idf = obj + ".id"
+        # api.o embeds the build id of the WHOLE tree: it is recompiled whenever anything changed
+        if name != "api.o" and not force and os.path.exists(obj) and os.path.exists(idf) and open(idf).read() == key:
+            return ""
+        out = _run(cmd)
+        with open(idf, "w") as f:
+            f.write(key)
+        return out
+
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs) + 1, os.cpu_count() or 4)) as ex:
-        for out in ex.map(lambda j: _run(j[1]), jobs + [shim_job]):
+        for out in ex.map(compile_job, jobs + [shim_job]):
             if verbose and out.strip():
                 print(out)
     _run([nvcc, "-shared", "-o", LIB, *[j[0] for j in jobs], "-gencode", "arch=compute_100a,code=sm_100a"])

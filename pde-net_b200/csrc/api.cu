@@ -2,6 +2,7 @@
 // everything is ordered on the caller's stream.
 #include "../../include/pdenet_b200.h"
 #include "launch.cuh"
+#include "linear_cluster_kernels.cuh"
 #include "small_kernels.cuh"
 
 #include <atomic>
@@ -846,6 +847,78 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
 }
 
 // ---- PDE-Net 1 linear rollout (row a12) ------------------------------------------------------
+// Small grids: one trajectory per thread-block cluster, resident in shared memory over all steps
+// (linear_cluster_kernels.cuh).  lin_cluster_plan returns the CTAs per cluster (1, 2, 4 or 8) or 0 when the
+// grid does not fit (then the tiled kernels run).
+static std::atomic<int> g_linear_cluster_on{1};
+
+struct LinClusterPlan {
+  int cs, pts, hb_max;
+  size_t smem;
+};
+static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, int N, int sms) {
+  LinClusterPlan none = {0, 0, 0, 0};
+  if (!g_linear_cluster_on.load(std::memory_order_relaxed) || (k != 3 && k != 5 && k != 7)) return none;
+  const int r = (k - 1) / 2, kk = k * k, pts_max = k == 7 ? 1 : 2;
+  auto fits = [&](int cs, LinClusterPlan &pl) {
+    if (H / cs < r || H / cs < 1) return false; // every band must own the halo rows its neighbours fetch
+    const int hb_max = (H + cs - 1) / cs;
+    if ((long long)hb_max * W > (long long)kLinClusterThreads * pts_max) return false;
+    const size_t elems = (size_t)(N + 1) * kk + (size_t)(hb_max + 2 * r) * kk * W + 3 * (size_t)(hb_max + 2 * r) * W;
+    if (elems * es > (size_t)220 * 1024) return false;
+    pl.cs = cs;
+    pl.hb_max = hb_max;
+    pl.pts = (hb_max * W + kLinClusterThreads - 1) / kLinClusterThreads;
+    pl.smem = elems * es;
+    return true;
+  };
+  LinClusterPlan best = none, cand;
+  for (int cs = 1; cs <= 8; cs *= 2)
+    if (fits(cs, cand)) {
+      if (!best.cs) best = cand;                                  // smallest cluster that fits ...
+      else if ((long long)B * cs <= sms) best = cand;             // ... widened while SMs would otherwise idle
+    }
+  return best;
+}
+
+template <typename KernelT, typename ParamsT>
+static int launch_cluster(KernelT kern, const ParamsT &p, int grid, int cs, size_t smem, cudaStream_t st) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return PDENET_E_CUDA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kLinClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p) == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+#define PDENET_LIN_CLUSTER_DISPATCH(KERNEL, k, pts, ...)                                                          \
+  do {                                                                                                            \
+    if (k == 3 && pts == 1) return launch_cluster(KERNEL<T, 3, 1>, __VA_ARGS__);                                  \
+    if (k == 3 && pts == 2) return launch_cluster(KERNEL<T, 3, 2>, __VA_ARGS__);                                  \
+    if (k == 5 && pts == 1) return launch_cluster(KERNEL<T, 5, 1>, __VA_ARGS__);                                  \
+    if (k == 5 && pts == 2) return launch_cluster(KERNEL<T, 5, 2>, __VA_ARGS__);                                  \
+    if (k == 7 && pts == 1) return launch_cluster(KERNEL<T, 7, 1>, __VA_ARGS__);                                  \
+    return PDENET_E_UNSUPPORTED;                                                                                  \
+  } while (0)
+
+template <typename T>
+static int lin_cluster_fwd_launch(const LinClusterParams<T> &p, int k, const LinClusterPlan &pl, cudaStream_t st) {
+  PDENET_LIN_CLUSTER_DISPATCH(linear_cluster_fwd_kernel, k, pl.pts, p, p.B * pl.cs, pl.cs, pl.smem, st);
+}
+template <typename T>
+static int lin_cluster_bwd_launch(const LinClusterParams<T> &p, int k, const LinClusterPlan &pl, cudaStream_t st) {
+  PDENET_LIN_CLUSTER_DISPATCH(linear_cluster_bwd_kernel, k, pl.pts, p, p.B * pl.cs, pl.cs, pl.smem, st);
+}
+
 template <typename T>
 static int linear_fwd(const T *u0, const T *id_kernel, const T *kernels, const T *coe, T *states, int B, int H,
                       int W, int k, int N, int steps, double dt, void *stream) {
@@ -853,6 +926,22 @@ static int linear_fwd(const T *u0, const T *id_kernel, const T *kernels, const T
     return PDENET_E_BADARG;
   if (!lin_supported(N + 1)) return PDENET_E_UNSUPPORTED;
   const size_t stride = (size_t)B * H * W;
+  if (steps > 0) {
+    const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sm_count());
+    if (pl.cs) { // small grid: the whole rollout in one launch, one trajectory per cluster
+      LinClusterParams<T> q;
+      memset(&q, 0, sizeof(q));
+      q.u0 = u0;
+      q.k0 = id_kernel;
+      q.kernels = kernels;
+      q.coe = coe;
+      q.states = states;
+      q.B = B, q.H = H, q.W = W, q.N = N, q.steps = steps, q.cs = pl.cs, q.hb_max = pl.hb_max;
+      q.dt = (T)dt;
+      ProfScope ps(0, (cudaStream_t)stream);
+      return lin_cluster_fwd_launch<T>(q, k, pl, (cudaStream_t)stream);
+    }
+  }
   SlotLease lease((cudaStream_t)stream);
   if (int rc = upload<T>(lease, id_kernel, kernels, N, k, (cudaStream_t)stream)) return rc;
   StepParams<T> p;
@@ -893,7 +982,9 @@ static LinLayout lin_layout(size_t es, int B, int H, int W, int k, int N, int sm
   o = align_up(o + (size_t)l.dk_slots * (N + 1) * l.vlb * sizeof(double), 256);
   l.off_dcoe = o;
   o = align_up(o + (size_t)B * N * img * es, 256);
-  l.total = o;
+  // the small-grid cluster path keeps its tap correlations R [B][k*k][H][W] + their batch sum here instead
+  const size_t cluster_need = align_up((size_t)(B + 1) * kk * img * es, 256);
+  l.total = o > cluster_need ? o : cluster_need;
   return l;
 }
 
@@ -921,12 +1012,44 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   const LinLayout lay = lin_layout(sizeof(T), B, H, W, k, N, sms);
   if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
   char *ws = (char *)workspace;
+  const size_t img = (size_t)H * W;
+  const size_t stride = (size_t)B * img;
+  {
+    const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms);
+    if (pl.cs) { // small grid: reverse rollout in one launch + two finishing kernels
+      const int kk = k * k;
+      LinClusterParams<T> q;
+      memset(&q, 0, sizeof(q));
+      q.u0 = u0;
+      q.k0 = id_kernel;
+      q.kernels = kernels;
+      q.coe = coe;
+      q.states = const_cast<T *>(states);
+      q.grad_states = grad_states;
+      q.grad_all = grad_mode == PDENET_GRAD_ALL;
+      q.grad_u0 = grad_u0;
+      q.R = (T *)ws;
+      q.B = B, q.H = H, q.W = W, q.N = N, q.steps = steps, q.cs = pl.cs, q.hb_max = pl.hb_max;
+      q.dt = (T)dt;
+      {
+        ProfScope ps(1, st);
+        if (int rc = lin_cluster_bwd_launch<T>(q, k, pl, st)) return rc;
+      }
+      if (grad_id_kernel || grad_kernels || grad_coe) {
+        T *Rsum = (T *)ws + (size_t)B * kk * img;
+        ProfScope ps(4, st);
+        lin_cluster_dcoe_kernel<T><<<(unsigned)((img + 127) / 128), 128, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
+                                                                                  grad_coe);
+        if (grad_id_kernel || grad_kernels)
+          lin_cluster_dk_kernel<T><<<dim3(kk, N + 1), 256, 0, st>>>(Rsum, coe, img, kk, (T)dt, grad_id_kernel, grad_kernels);
+      }
+      return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+    }
+  }
   T *gbuf = (T *)(ws + lay.off_g);
   T *lamb[2] = {(T *)(ws + lay.off_lam0), (T *)(ws + lay.off_lam1)};
   double *dkp = (double *)(ws + lay.off_dk);
   T *dcoe = (T *)(ws + lay.off_dcoe);
-  const size_t img = (size_t)H * W;
-  const size_t stride = (size_t)B * img;
   const bool want_dk = grad_id_kernel != nullptr || grad_kernels != nullptr;
   if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * (N + 1) * lay.vlb * sizeof(double), st) != cudaSuccess ||
       cudaMemsetAsync(dcoe, 0, (size_t)B * N * img * sizeof(T), st) != cudaSuccess)
@@ -1656,6 +1779,11 @@ int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef
                               double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
                               void *st) {
   return lagrange1d_bwd<float>(x, gy, coef, gx, gcoef, n, lo, hi, mesh, degree, workspace, workspace_bytes, st);
+}
+
+int pdenet_linear_small_grid_path(int on) {
+  const int prev = g_linear_cluster_on.exchange(on != 0 ? 1 : 0);
+  return prev;
 }
 
 int pdenet_profile_enable(int on) {

@@ -617,7 +617,19 @@ def test_polypde2d_module_matches_oracle(P, cuda_device):
                                                     (3, 1, 2, 9, 8, 2),
                                                     (5, 2, 2, 29, 65, 2)])  # H % 4 == 1, W % 64 == 1: last strip is the last row
 @pytest.mark.parametrize("grad_all", [False, True])
-def test_linear_rollout(P, cuda_device, k, max_order, B, H, W, steps, grad_all):
+@pytest.mark.parametrize("small_path", [True, False])
+def test_linear_rollout(P, cuda_device, k, max_order, B, H, W, steps, grad_all, small_path):
+    """small_path: the cluster-resident small-grid kernels (one launch per direction, state in shared memory,
+    DSMEM halos, folded stencil) where the grid fits them / the tiled kernels for every size."""
+    from pdenet_b200 import _lib
+    prev = _lib.lib().pdenet_linear_small_grid_path(1 if small_path else 0)
+    try:
+        _linear_rollout_case(P, cuda_device, k, max_order, B, H, W, steps, grad_all)
+    finally:
+        _lib.lib().pdenet_linear_small_grid_path(prev)
+
+
+def _linear_rollout_case(P, cuda_device, k, max_order, B, H, W, steps, grad_all):
     g = torch.Generator().manual_seed(31)
     orders = [o for o in O.order_list(max_order) if o != (0, 0)]
     N = len(orders)
@@ -645,6 +657,55 @@ def test_linear_rollout(P, cuda_device, k, max_order, B, H, W, steps, grad_all):
     assert rel(out, ref) < 1e-10 * steps
     for name, a, b in zip(["u0", "K0", "Ks", "coe"], dl, leaves):
         assert rel(a.grad, b.grad) < 1e-10 * steps, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_linear_small_grid_path_config2_shape(P, cuda_device, dtype):
+    """BASELINE config 2 at its size (50 x 50, 5 x 5 filters, max_order 4 = 15 filters + D0, batch 16): the cluster
+    path (one forward launch, one reverse launch + two finishing kernels) against the tiled path in fp64.
+    fp64: 20 dt-blocks, equal to re-association.  fp32: 5 blocks, state within 1e-5 per step, gradients within
+    the stated conditioning factor of the 1/dx^4-scaled taps (fp32_grad_scale)."""
+    from pdenet_b200 import _lib, ops
+    k, max_order, B, H, W = 5, 4, 16, 50, 50
+    steps = 20 if dtype == torch.float64 else 5
+    g = torch.Generator().manual_seed(41)
+    orders = [o for o in O.order_list(max_order) if o != (0, 0)]
+    N = len(orders)
+    dx = 2 * math.pi / W
+    dt = 1.5e-2 * dx * dx
+    M = O.initial_moments(k, orders) + 1e-3 * torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    Ks = O.scaled_kernels(M, O.filter_scales(orders, dx))
+    K0 = O.m2k(O.initial_moments(k, [(0, 0)]) + 1e-3 * torch.randn(1, k, k, generator=g, dtype=torch.float64))[0]
+    # coefficient fields scaled so that every term dt * c_n * D_n stays O(1e-2) (random O(1) coefficients on the
+    # 3rd / 4th derivatives blow up to 1e24 within 20 steps)
+    amp = torch.tensor([0.5 * dx ** max(0, o0 + o1 - 2) for (o0, o1) in orders], dtype=torch.float64)
+    coe = amp[:, None, None] * torch.randn(N, H, W, generator=g, dtype=torch.float64)
+    u0 = smooth_field(B, 1, H, W, 42)[:, 0]
+
+    def run(dt_, on):
+        prev = _lib.lib().pdenet_linear_small_grid_path(on)
+        try:
+            leaves = [t.to(cuda_device, dt_).clone().requires_grad_(True) for t in (u0, K0, Ks, coe)]
+            ops.profile_read()
+            out = P.linear_rollout(*leaves, dt, steps, last_only=True)
+            out.square().mean().backward()
+            torch.cuda.synchronize()
+            return [out.detach()] + [t.grad for t in leaves], ops.profile_read()[1]
+        finally:
+            _lib.lib().pdenet_linear_small_grid_path(prev)
+
+    ref, n_tiled = run(torch.float64, 0)
+    got, n_small = run(dtype, 1)
+    assert n_small["fwd_step"] == 1 and n_small["bwd_kernel_A"] == 1 and n_small["bwd_kernel_B1"] == 0
+    assert n_tiled["fwd_step"] == steps
+    names = ["state", "grad_u0", "grad_K0", "grad_Ks", "grad_coe"]
+    if dtype == torch.float64:
+        for n, a, b in zip(names, got, ref):
+            assert rel(a, b) < 1e-11, (n, rel(a, b))
+    else:
+        gscale = fp32_grad_scale(Ks)
+        for n, a, b in zip(names, got, ref):
+            assert rel(a, b) < 1e-5 * steps * (1.0 if n == "state" else gscale), (n, rel(a, b))
 
 
 def test_variantcoe_module_with_interpolated_fields(P, cuda_device):
