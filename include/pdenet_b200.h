@@ -350,6 +350,15 @@ PDENET_API int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const 
                               double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
                               void *stream);
 
+/* ---- tile policy ---------------------------------------------------------------------------------
+ * The step / data-gradient / filter-gradient kernels exist with large tiles (64 x 32..64 points: the headline
+ * grids) and with small tiles (32 x 16 / 64 x 16: grids whose large-tile count would leave SMs idle or badly
+ * balanced -- BASELINE configs 1 and 3).  A launch uses the small tiles when it has fewer than `factor` large
+ * tiles per resident CTA slot (default 4; environment PDENET_SMALL_TILE_FACTOR; 0 = always large tiles).
+ * Results are identical bit for bit (same per-point arithmetic; the partial sums of the parameter gradients are
+ * grouped differently, fixed order either way).  Returns the previous factor; a negative argument only queries. */
+PDENET_API int pdenet_small_tile_factor(int factor);
+
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),
  * 2 = reverse kernel B1 (data gradient), 3 = reverse kernel B2 (filter gradient),

@@ -19,9 +19,11 @@
 
 namespace pdenet {
 
-template <typename T, int K> struct AdjCfg {
+// NT_ = 256: 64-row tiles, two CTAs per SM.  NT_ = 64: the SMALL tile (16 rows, eight CTAs per SM) for problems
+// with too few large tiles to fill / balance the SMs.
+template <typename T, int K, int NT_ = 256> struct AdjCfg {
   static constexpr int R = (K - 1) / 2;
-  static constexpr int NT = 256;
+  static constexpr int NT = NT_;
   static constexpr int VEC = VecOf<T>::N;
   static constexpr int RW = 8;
   static constexpr int TW = 32 * VEC, TH = RW * (NT / 32);
@@ -39,8 +41,9 @@ template <typename T, int K> struct AdjCfg {
   static __host__ size_t smem_bytes(int) { return (size_t)(2 * TILE_ELEMS) * sizeof(T); }
 };
 
-template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_kernel(const AdjParams<T> p) {
-  using Cfg = AdjCfg<T, K>;
+template <typename T, int K, int NT_ = 256>
+__global__ void __launch_bounds__(NT_, NT_ == 256 ? 2 : 8) adjoint_kernel(const AdjParams<T> p) {
+  using Cfg = AdjCfg<T, K, NT_>;
   constexpr int R = Cfg::R, NT = Cfg::NT, VEC = Cfg::VEC, RW = Cfg::RW, TW = Cfg::TW, TH = Cfg::TH;
   constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK;
   constexpr int TILE = Cfg::TILE_ELEMS;
@@ -235,11 +238,12 @@ template <typename T, int K> __global__ void __launch_bounds__(256, 2) adjoint_k
 }
 
 // --------------------------------------------------------------------------------------------
-template <typename T, int K> struct FGradCfg {
+// MT_ = 8: 64-row tiles.  MT_ = 2: the SMALL tile (16 rows) for problems with too few large tiles.
+template <typename T, int K, int MT_ = 8> struct FGradCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int VEC = VecOf<T>::N;
   static constexpr int RW = 8;
-  static constexpr int MT = 8; // micro-tiles (of RW rows) per lane per tile
+  static constexpr int MT = MT_; // micro-tiles (of RW rows) per lane per tile
   static constexpr int TW = 32 * VEC, TH = RW * MT;
   static constexpr int NV = (VEC + K - 1 + VEC - 1) / VEC;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
@@ -254,9 +258,9 @@ template <typename T, int K> struct FGradCfg {
   static __host__ size_t smem_bytes() { return (size_t)(2 * TILE_ELEMS + (NT / 32) * GST_ELEMS) * sizeof(T); }
 };
 
-template <typename T, int K>
-__global__ void __launch_bounds__(FGradCfg<T, K>::NT, kFGradCtasPerSm) filter_grad_kernel(const FGradParams<T> p) {
-  using Cfg = FGradCfg<T, K>;
+template <typename T, int K, int MT_ = 8>
+__global__ void __launch_bounds__(FGradCfg<T, K, MT_>::NT, kFGradCtasPerSm) filter_grad_kernel(const FGradParams<T> p) {
+  using Cfg = FGradCfg<T, K, MT_>;
   constexpr int NTHREADS = Cfg::NT;
   constexpr int R = Cfg::R, VEC = Cfg::VEC, RW = Cfg::RW, MT = Cfg::MT, TW = Cfg::TW, TH = Cfg::TH;
   constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK, VLB = Cfg::VLB;

@@ -8,12 +8,20 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
 
 namespace pdenet {
+
+// small-tile policy (params.cuh): process-global, settable through pdenet_small_tile_factor()
+static std::atomic<int> g_small_tile_factor{[] {
+  const char *e = getenv("PDENET_SMALL_TILE_FACTOR");
+  return e ? atoi(e) : 4;
+}()};
+int small_tile_factor() { return g_small_tile_factor.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // measurement hooks: launch counters (always) + per-launch event pairs (when enabled)
@@ -58,13 +66,13 @@ struct ProfScope {
 // extern templates: the heavy kernels live in inst_<type>_k<K>.o
 #define PDENET_EXTERN(TT, KK)                                                                                     \
   extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
-  extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, cudaStream_t);                          \
+  extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, int, cudaStream_t);                     \
   extern template int upload_taps<TT, KK>(int, int, const TT *, int, cudaStream_t);                              \
   extern template size_t step_smem_bytes<TT, KK>(int, int, int, int);                                            \
-  extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, cudaStream_t);                    \
-  extern template void filter_grad_tile<TT, KK>(int &, int &);                                                   \
+  extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, int, cudaStream_t);               \
+  extern template void filter_grad_tile<TT, KK>(int, int &, int &);                                              \
   extern template int adjoint_vlb<TT, KK>();                                                                     \
-  extern template void adjoint_tile<TT, KK>(int &, int &);
+  extern template void adjoint_tile<TT, KK>(int, int &, int &);
 PDENET_EXTERN(double, 3) PDENET_EXTERN(double, 5) PDENET_EXTERN(double, 7)
 PDENET_EXTERN(float, 3) PDENET_EXTERN(float, 5) PDENET_EXTERN(float, 7)
 #undef PDENET_EXTERN
@@ -356,24 +364,28 @@ static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int
 
 template <typename T, int K>
 static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaStream_t st) {
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
   int tw, th;
-  adjoint_tile<T, K>(tw, th);
+  adjoint_tile<T, K>(0, tw, th);
   p.B = B;
   p.C = C;
   p.N = N;
   p.H = H;
   p.W = W;
+  // small (16-row) tiles when the 64-row tiles would be too few to fill / balance the SMs
+  const long long big_items = (long long)B * C * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+  const int small = p.wrap_y && !p.mirror_rows && big_items < (long long)small_tile_factor() * sms * 2;
+  if (small) adjoint_tile<T, K>(1, tw, th);
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.n_items = B * C * p.tiles_x * p.tiles_y;
   const int vec = 16 / (int)sizeof(T);
   p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
-  const int sms = sm_count();
-  if (sms <= 0) return PDENET_E_CUDA;
-  const int cap = sms * 2; // two resident CTAs per SM
+  const int cap = sms * (small ? 8 : 2); // resident CTAs per SM
   const int grid = p.n_items < cap ? p.n_items : cap;
   ProfScope ps(2, st);
-  return launch_adjoint<T, K>(p, grid, st);
+  return launch_adjoint<T, K>(p, grid, small, st);
 }
 
 // Filter gradient: warps own filters; N filters are covered by launches of nw in {6, 3, 2, 1}
@@ -383,20 +395,23 @@ static int dk_slot_count(int sms) { return sms * kFGradCtasPerSm * kFGradWarps; 
 
 template <typename T, int K>
 static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W, cudaStream_t st) {
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
   int tw, th;
-  filter_grad_tile<T, K>(tw, th);
+  filter_grad_tile<T, K>(0, tw, th);
   p.B = B;
   p.C = C;
   p.N = N;
   p.H = H;
   p.W = W;
+  const long long big_items = (long long)B * C * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+  const int small = p.wrap_y && big_items < (long long)small_tile_factor() * sms * kFGradCtasPerSm;
+  if (small) filter_grad_tile<T, K>(1, tw, th);
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.n_items = B * C * p.tiles_x * p.tiles_y;
   const int vec = 16 / (int)sizeof(T);
   p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
-  const int sms = sm_count();
-  if (sms <= 0) return PDENET_E_CUDA;
   const int cap = sms * kFGradCtasPerSm;
   const int grid = p.n_items < cap ? p.n_items : cap;
   int n0 = 0;
@@ -408,7 +423,7 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
     p.n0 = n0;
     p.nw = nw;
     ProfScope ps(3, st);
-    const int rc = launch_filter_grad<T, K>(p, grid, st);
+    const int rc = launch_filter_grad<T, K>(p, grid, small, st);
     if (rc) return rc;
     n0 += nw;
   }
@@ -567,7 +582,7 @@ static SlabLayout slab_layout(size_t es, int B, int C, int Hs, int W, int k, int
   const int kk = k * k, r = (k - 1) / 2;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
   l.dk_slots = dk_slot_count(sms);
-  l.sym_slots = sms;
+  l.sym_slots = sms * kSymSlotsPerSm;
   size_t o = 0;
   l.off_g = o;
   o = align_up(o + (size_t)B * C * N * (Hs + 2 * r) * W * es, 256);
@@ -701,7 +716,7 @@ static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N,
   const int kk = k * k;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
   l.dk_slots = dk_slot_count(sms);
-  l.sym_slots = sms;
+  l.sym_slots = sms * kSymSlotsPerSm;
   const size_t img = (size_t)H * W;
   size_t o = 0;
   l.off_g = o;
@@ -1779,6 +1794,11 @@ int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef
                               double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
                               void *st) {
   return lagrange1d_bwd<float>(x, gy, coef, gx, gcoef, n, lo, hi, mesh, degree, workspace, workspace_bytes, st);
+}
+
+int pdenet_small_tile_factor(int factor) {
+  if (factor < 0) return g_small_tile_factor.load();
+  return g_small_tile_factor.exchange(factor);
 }
 
 int pdenet_linear_small_grid_path(int on) {

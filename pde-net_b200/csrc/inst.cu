@@ -18,25 +18,42 @@ template <typename KernelT> static int allow_smem(KernelT kern, size_t smem) {
 
 constexpr size_t kMaxDynamicSmem = 227 * 1024;
 
-template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1>
+template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1, int NTO = 0>
 static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
-  using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads(MODE, C * N))>;
   StepParams<T> p = p_in;
   p.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
   p.n_items = p.B * p.tiles_x * p.tiles_y;
-  const int grid = p.n_items < sms ? p.n_items : sms;
+  const int slots = sms * (NTO ? kSmallTileCtasPerSm : 1);
+  const int grid = p.n_items < slots ? p.n_items : slots;
   constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT || MODE == MODE_UPW_BWD_A;
   const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);
   if (smem > kMaxDynamicSmem) return -2; // e.g. 3-channel banks with deep SymNets in the recomputing reverse kernel
-  auto kern = step_kernel<T, K, N, C, MODE, VL, LT>;
+  auto kern = step_kernel<T, K, N, C, MODE, VL, LT, NTO>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// Small tiles (32 x 16 in fp64) are compiled for the headline bank (N = 6, C = 2, 2-layer SymNet) and used when
+// the large tiles would be too few to fill / balance the SMs: fewer than kSmallTileFactor items per SM.
+template <typename T, int K>
+static bool want_small_tiles(int mode, int N, int C, int VL, const StepParams<T> &p, int sms) {
+  if (!(N == 6 && C == 2 && p.L == 2 && VL == 16) || p.mirror_rows || !p.wrap_y) return false;
+  if (!(mode == MODE_FWD || mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT)) return false;
+  using Big = StepCfg<T, K, 6, 2, step_threads(MODE_FWD, 12)>;
+  const long long items = (long long)p.B * ((p.W + Big::TW - 1) / Big::TW) * ((p.H + Big::TH - 1) / Big::TH);
+  return items < (long long)small_tile_factor() * sms;
+}
+
 template <typename T, int K>
 int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st) {
+  if (want_small_tiles<T, K>(mode, N, C, VL, p, sms)) {
+    if (mode == MODE_FWD) return launch_step_one<T, K, 6, 2, MODE_FWD, 16, 2, 128>(p, sms, st);
+    if (mode == MODE_BWD_A) return launch_step_one<T, K, 6, 2, MODE_BWD_A, 16, 2, 128>(p, sms, st);
+    if (mode == MODE_BWD_A_KEPT) return launch_step_one<T, K, 6, 2, MODE_BWD_A_KEPT, 16, 2, 128>(p, sms, st);
+  }
 #define PDENET_CASE(NN, CC)                                                                                       \
   if (N == NN && C == CC) {                                                                                      \
     if (mode == MODE_FWD) {                                                                                      \
@@ -98,27 +115,35 @@ template <typename T, int K> size_t step_smem_bytes(int mode, int N, int C, int 
   return 0;
 }
 
-template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st) {
-  using Cfg = AdjCfg<T, K>;
+// `small` selects the 16-row tile variants; the caller sizes tiles_x/tiles_y/n_items with adjoint_tile /
+// filter_grad_tile of the same variant
+template <typename T, int K, int NT_> static int launch_adjoint_v(const AdjParams<T> &p, int grid, cudaStream_t st) {
+  using Cfg = AdjCfg<T, K, NT_>;
   const size_t smem = Cfg::smem_bytes(p.N);
   if (smem > 227 * 1024) return -2;
-  auto kern = adjoint_kernel<T, K>;
+  auto kern = adjoint_kernel<T, K, NT_>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, int small, cudaStream_t st) {
+  return small ? launch_adjoint_v<T, K, 64>(p, grid, st) : launch_adjoint_v<T, K, 256>(p, grid, st);
 }
 
-template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st) {
-  using Cfg = FGradCfg<T, K>;
+template <typename T, int K, int MT_> static int launch_filter_grad_v(const FGradParams<T> &p, int grid, cudaStream_t st) {
+  using Cfg = FGradCfg<T, K, MT_>;
   const size_t smem = Cfg::smem_bytes();
-  auto kern = filter_grad_kernel<T, K>;
+  auto kern = filter_grad_kernel<T, K, MT_>;
   if (allow_smem(kern, smem) != 0) return -4;
   kern<<<grid, Cfg::NT, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
-template <typename T, int K> void filter_grad_tile(int &tw, int &th) {
+template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, int small, cudaStream_t st) {
+  return small ? launch_filter_grad_v<T, K, 2>(p, grid, st) : launch_filter_grad_v<T, K, 8>(p, grid, st);
+}
+template <typename T, int K> void filter_grad_tile(int small, int &tw, int &th) {
   tw = FGradCfg<T, K>::TW;
-  th = FGradCfg<T, K>::TH;
+  th = small ? FGradCfg<T, K, 2>::TH : FGradCfg<T, K, 8>::TH;
 }
 
 template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st) {
@@ -132,18 +157,18 @@ template <typename T, int K> int upload_taps(int slot, int first, const T *taps,
 }
 
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
-template <typename T, int K> void adjoint_tile(int &tw, int &th) {
+template <typename T, int K> void adjoint_tile(int small, int &tw, int &th) {
   tw = AdjCfg<T, K>::TW;
-  th = AdjCfg<T, K>::TH;
+  th = small ? AdjCfg<T, K, 64>::TH : AdjCfg<T, K, 256>::TH;
 }
 
 template int launch_step<PDENET_T, PDENET_K>(int, int, int, int, const StepParams<PDENET_T> &, int, cudaStream_t);
 template size_t step_smem_bytes<PDENET_T, PDENET_K>(int, int, int, int);
-template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int, cudaStream_t);
-template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, cudaStream_t);
-template void filter_grad_tile<PDENET_T, PDENET_K>(int &, int &);
+template int launch_adjoint<PDENET_T, PDENET_K>(const AdjParams<PDENET_T> &, int, int, cudaStream_t);
+template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> &, int, int, cudaStream_t);
+template void filter_grad_tile<PDENET_T, PDENET_K>(int, int &, int &);
 template int adjoint_vlb<PDENET_T, PDENET_K>();
 template int upload_taps<PDENET_T, PDENET_K>(int, int, const PDENET_T *, int, cudaStream_t);
-template void adjoint_tile<PDENET_T, PDENET_K>(int &, int &);
+template void adjoint_tile<PDENET_T, PDENET_K>(int, int &, int &);
 
 } // namespace pdenet

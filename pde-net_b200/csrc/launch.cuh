@@ -17,14 +17,14 @@ namespace pdenet {
 // tile decomposition from p.B/H/W and launches min(items, sms) persistent CTAs
 template <typename T, int K>
 int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st);
-template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, cudaStream_t st);
+template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, int small, cudaStream_t st);
 // dynamic shared memory (bytes) a step kernel of this bank needs in `mode`; 0 if the bank is not compiled
 template <typename T, int K> size_t step_smem_bytes(int mode, int N, int C, int Psym);
-template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, cudaStream_t st);
-template <typename T, int K> void filter_grad_tile(int &tw, int &th);
+template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, int small, cudaStream_t st);
+template <typename T, int K> void filter_grad_tile(int small, int &tw, int &th);
 template <typename T, int K> int adjoint_vlb();
 // copy n_filters [K][K] filters (device memory) into constant slot `slot`, starting at filter index `first`
 template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st);
-template <typename T, int K> void adjoint_tile(int &tw, int &th);
+template <typename T, int K> void adjoint_tile(int small, int &tw, int &th);
 
 } // namespace pdenet

@@ -58,6 +58,13 @@ __host__ __device__ constexpr int step_threads(int mode, int M) {
                                                                                                                : 256;
 }
 
+// Small-tile variants (see StepCfg): two 128-thread CTAs per SM; per-CTA partial-sum slots are sized for them.
+constexpr int kSmallTileCtasPerSm = 2;
+constexpr int kSymSlotsPerSm = kSmallTileCtasPerSm;
+// large-tile items per SM below which the small tiles are used (pdenet_small_tile_factor() sets it; 0 = never;
+// initial value from PDENET_SMALL_TILE_FACTOR, default 4).  Defined in api.cu.
+int small_tile_factor();
+
 template <typename T> struct AdjParams {
   const T *g; // [B][C*N][g_rows][W]
   int g_rows, g_off;

@@ -28,7 +28,11 @@ template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
   // load has to feed twice as many FMAs to stay off the issue-slot limit) when the C*N features of
   // 8 points still fit the register file
   static constexpr int P = (sizeof(T) == 4 && C * N <= 12) ? 8 : 4;
-  static constexpr int TW = 64, TH = (NT / 64) * 2 * P; // 2 warps across, NT/64 down, 2 strips of P rows each
+  // warp layout of a tile: WA warps across (32 columns each), WD down, SPW strips of P rows per warp.
+  // NT >= 256: the large tile, 64 x (NT/64 * 2P).  NT == 128: the SMALL tile, 32 x 4P (four warps stacked),
+  // for problems whose large-tile count would leave SMs idle or badly balanced (BASELINE configs 1 and 3).
+  static constexpr int WA = NT >= 256 ? 2 : 1, WD = NT / 32 / WA, SPW = NT >= 256 ? 2 : 1;
+  static constexpr int TW = 32 * WA, TH = WD * SPW * P;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH = SC;
   static constexpr int VEC = VecOf<T>::N;
@@ -638,9 +642,10 @@ __device__ __forceinline__ void upwind_reverse_half(T (&d)[MD][P], const T *syms
 }
 
 // --------------------------------------------------------------------------------------------
-template <typename T, int K, int N, int C, int MODE, int VL, int LT>
-__global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const StepParams<T> p) {
-  using Cfg = StepCfg<T, K, N, C, step_threads(MODE, C * N)>;
+// NTO: 0 = the large tile with step_threads(MODE, C*N) threads, one CTA per SM; 128 = the small tile, two CTAs per SM
+template <typename T, int K, int N, int C, int MODE, int VL, int LT, int NTO = 0>
+__global__ void __launch_bounds__(NTO ? NTO : step_threads(MODE, C *N), NTO ? 2 : 1) step_kernel(const StepParams<T> p) {
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads(MODE, C * N))>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
@@ -681,7 +686,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     cp_async_commit();
   }
 
-  const int wx = warp & 1, wy = warp >> 1;
+  const int wx = warp % Cfg::WA, wy = warp / Cfg::WA;
   double *sg = sgrad + warp * Cfg::grad_elems(Psym);
   constexpr int region = Cfg::tile_region(KEPT);
   T *scratch = tiles + region + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (reverse)
@@ -691,7 +696,7 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
   }
 
-  constexpr int SPW = TH / ((NT / 64) * P); // strips per warp and item
+  constexpr int SPW = Cfg::SPW;             // strips per warp and item
   if constexpr (KEPT) __syncthreads();      // setup (SymNet parameters, zeroed accumulators, tables) visible to all
   for (; item < p.n_items; item += gridDim.x) {
     // One barrier per item: this item's tile has landed for every thread and every warp has
@@ -710,8 +715,8 @@ __global__ void __launch_bounds__(step_threads(MODE, C *N), 1) step_kernel(const
     const int x = tx * TW + col;
 
 #pragma unroll 1
-    for (int s = 0; s < TH / ((NT / 64) * P); ++s) {
-      const int row0 = (wy * (TH / ((NT / 64) * P)) + s) * P;
+    for (int s = 0; s < SPW; ++s) {
+      const int row0 = (wy * SPW + s) * P;
       const int y0 = ty * TH + row0;
       if (y0 >= H) break; // warp-uniform: the rest of this warp's strips lie below the grid (ragged last tile row)
       bool valid[P];

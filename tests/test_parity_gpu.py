@@ -132,7 +132,7 @@ def test_fd2d_features(P, cuda_device, k, max_order, C, H, W, dtype):
     assert (err <= bound).all(), (err / bound).tolist()
 
 
-def test_fd2d_autograd(P, cuda_device):
+def test_fd2d_autograd(P, cuda_device, tile_policy):
     k, C, H, W = 5, 2, 21, 34
     orders, M, scales, _ = make_model(k, 2, C, 0, 0.5, 5)
     Ks = O.scaled_kernels(M, scales)
@@ -179,7 +179,7 @@ EDGE_CASES = [
 
 @pytest.mark.parametrize("case", EDGE_CASES)
 @pytest.mark.parametrize("keep", [False, True])
-def test_rollout_parity_edge_shapes(P, cuda_device, case, keep):
+def test_rollout_parity_edge_shapes(P, cuda_device, case, keep, tile_policy):
     got, ref = run_both(P, cuda_device, case, torch.float64, True, keep=keep)
     steps = case[7]
     for n, a, b in zip(["states", "grad_u0", "grad_kernels", "grad_symnet"], got, ref):
@@ -232,10 +232,20 @@ def run_both(P, dev, case, dtype, grad_all, batch_chunk=0, keep=None):
     return (st, ud.grad, Kd.grad, sd.grad), (st_ref, uc.grad, Kc.grad, sc.grad)
 
 
+@pytest.fixture(params=["small_tiles_when_few_items", "large_tiles_always"])
+def tile_policy(request, cuda_device):
+    """Run a test under both tile policies: the default (small 16-row tiles when a launch has few large tiles --
+    nearly every shape of this suite) and large tiles for every shape (pdenet_small_tile_factor(0))."""
+    from pdenet_b200 import _lib
+    prev = _lib.lib().pdenet_small_tile_factor(4 if request.param.startswith("small") else 0)
+    yield request.param
+    _lib.lib().pdenet_small_tile_factor(prev)
+
+
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("grad_all", [False, True])
 @pytest.mark.parametrize("keep", [False, True])
-def test_rollout_parity_fp64(P, cuda_device, case, grad_all, keep):
+def test_rollout_parity_fp64(P, cuda_device, case, grad_all, keep, tile_policy):
     got, ref = run_both(P, cuda_device, case, torch.float64, grad_all, keep=keep)
     steps = case[7]
     names = ["states", "grad_u0", "grad_kernels", "grad_symnet"]
@@ -259,7 +269,7 @@ def oracle_fp32(case):
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("keep", [False, True])
-def test_rollout_parity_fp32(P, cuda_device, case, keep):
+def test_rollout_parity_fp32(P, cuda_device, case, keep, tile_policy):
     """fp32 against the fp64 oracle: states within 1e-5 per step; gradients within
     1e-5 * steps * fp32_grad_scale (the stated conditioning factor of the scaled taps)."""
     got, ref = run_both(P, cuda_device, case, torch.float32, True, keep=keep)
@@ -274,7 +284,7 @@ def test_rollout_parity_fp32(P, cuda_device, case, keep):
 
 @pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[6], EDGE_CASES[7]])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_kept_features_equal_recomputed_bitwise(P, cuda_device, case, dtype):
+def test_kept_features_equal_recomputed_bitwise(P, cuda_device, case, dtype, tile_policy):
     """The feature-keeping rollout (pdenet_rollout_fwd_keep / bwd_kept) stores exactly the values
     the plain reverse pass recomputes, so states and all gradients agree bit for bit."""
     a, _ = run_both(P, cuda_device, case, dtype, True, batch_chunk=2, keep=True)
