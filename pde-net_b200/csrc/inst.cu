@@ -20,7 +20,7 @@ constexpr size_t kMaxDynamicSmem = 227 * 1024;
 
 template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1, int NTO = 0>
 static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
-  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads(MODE, C * N))>;
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N)>;
   StepParams<T> p = p_in;
   p.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;

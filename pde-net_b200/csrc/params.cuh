@@ -65,6 +65,16 @@ constexpr int kSymSlotsPerSm = kSmallTileCtasPerSm;
 // initial value from PDENET_SMALL_TILE_FACTOR, default 4).  Defined in api.cu.
 int small_tile_factor();
 
+// fp32 kernel A on kept features: strips of 4 points (not 8) and 12 warps -- it runs no stencils, so nothing asks
+// for the long strip, and the halved register footprint (d[12][4] + S[10][4] floats) lets 12 warps hide its
+// global-load and shared-memory latencies (8 warps at 254 registers: 0.33 of the FP32 peak)
+template <typename T> __host__ __device__ constexpr int step_p_override(int mode, int M) {
+  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? 4 : 0;
+}
+template <typename T> __host__ __device__ constexpr int step_threads_t(int mode, int M) {
+  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? 384 : step_threads(mode, M);
+}
+
 template <typename T> struct AdjParams {
   const T *g; // [B][C*N][g_rows][W]
   int g_rows, g_off;

@@ -21,13 +21,14 @@ template <typename T> struct TransposeCfg {
   static constexpr int ELEMS = 32 * PITCH;
 };
 
-template <typename T, int K, int N, int C, int NT_ = 256> struct StepCfg {
+template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = NT_;
   // points per thread strip: 4 in fp64; 8 in fp32 (FFMA issues every cycle, so each uniform tap
   // load has to feed twice as many FMAs to stay off the issue-slot limit) when the C*N features of
   // 8 points still fit the register file
-  static constexpr int P = (sizeof(T) == 4 && C * N <= 12) ? 8 : 4;
+  // (PO overrides: see step_p_override)
+  static constexpr int P = PO ? PO : ((sizeof(T) == 4 && C * N <= 12) ? 8 : 4);
   // warp layout of a tile: WA warps across (32 columns each), WD down, SPW strips of P rows per warp.
   // NT >= 256: the large tile, 64 x (NT/64 * 2P).  NT == 128: the SMALL tile, 32 x 4P (four warps stacked),
   // for problems whose large-tile count would leave SMs idle or badly balanced (BASELINE configs 1 and 3).
@@ -644,8 +645,8 @@ __device__ __forceinline__ void upwind_reverse_half(T (&d)[MD][P], const T *syms
 // --------------------------------------------------------------------------------------------
 // NTO: 0 = the large tile with step_threads(MODE, C*N) threads, one CTA per SM; 128 = the small tile, two CTAs per SM
 template <typename T, int K, int N, int C, int MODE, int VL, int LT, int NTO = 0>
-__global__ void __launch_bounds__(NTO ? NTO : step_threads(MODE, C *N), NTO ? 2 : 1) step_kernel(const StepParams<T> p) {
-  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads(MODE, C * N))>;
+__global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO ? 2 : 1) step_kernel(const StepParams<T> p) {
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
