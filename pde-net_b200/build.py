@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
+NVCC_FLAGS += os.environ.get("PDENET_EXTRA_NVCC_FLAGS", "").split()   # experiments: -D... switches of the kernels
 TYPES = [("f64", "double"), ("f32", "float")]
 KS = [3, 5, 7]
 

@@ -25,7 +25,7 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
   p.n_items = p.B * p.tiles_x * p.tiles_y;
-  const int slots = sms * (NTO ? kSmallTileCtasPerSm : 1);
+  const int slots = sms * (NTO ? kSmallTileCtasPerSm : step_min_blocks<T>(MODE, C * N));
   const int grid = p.n_items < slots ? p.n_items : slots;
   constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT || MODE == MODE_UPW_BWD_A;
   const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);

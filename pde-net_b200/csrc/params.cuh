@@ -68,11 +68,18 @@ int small_tile_factor();
 // fp32 kernel A on kept features: strips of 4 points (not 8) and 12 warps -- it runs no stencils, so nothing asks
 // for the long strip, and the halved register footprint (d[12][4] + S[10][4] floats) lets 12 warps hide its
 // global-load and shared-memory latencies (8 warps at 254 registers: 0.33 of the FP32 peak)
+#ifndef PDENET_KEPT_F32_THREADS
+#define PDENET_KEPT_F32_THREADS 384
+#define PDENET_KEPT_F32_BLOCKS 1
+#endif
 template <typename T> __host__ __device__ constexpr int step_p_override(int mode, int M) {
   return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? 4 : 0;
 }
 template <typename T> __host__ __device__ constexpr int step_threads_t(int mode, int M) {
-  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? 384 : step_threads(mode, M);
+  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_THREADS : step_threads(mode, M);
+}
+template <typename T> __host__ __device__ constexpr int step_min_blocks(int mode, int M) {
+  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_BLOCKS : 1;
 }
 
 template <typename T> struct AdjParams {

@@ -645,7 +645,8 @@ __device__ __forceinline__ void upwind_reverse_half(T (&d)[MD][P], const T *syms
 // --------------------------------------------------------------------------------------------
 // NTO: 0 = the large tile with step_threads(MODE, C*N) threads, one CTA per SM; 128 = the small tile, two CTAs per SM
 template <typename T, int K, int N, int C, int MODE, int VL, int LT, int NTO = 0>
-__global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO ? 2 : 1) step_kernel(const StepParams<T> p) {
+__global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO ? 2 : step_min_blocks<T>(MODE, C *N))
+    step_kernel(const StepParams<T> p) {
   using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
