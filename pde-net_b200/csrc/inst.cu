@@ -139,11 +139,11 @@ template <typename T, int K, int MT_> static int launch_filter_grad_v(const FGra
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, int small, cudaStream_t st) {
-  return small ? launch_filter_grad_v<T, K, 2>(p, grid, st) : launch_filter_grad_v<T, K, 8>(p, grid, st);
+  return small ? launch_filter_grad_v<T, K, 2>(p, grid, st) : launch_filter_grad_v<T, K, kFGradMT>(p, grid, st);
 }
 template <typename T, int K> void filter_grad_tile(int small, int &tw, int &th) {
   tw = FGradCfg<T, K>::TW;
-  th = small ? FGradCfg<T, K, 2>::TH : FGradCfg<T, K, 8>::TH;
+  th = small ? FGradCfg<T, K, 2>::TH : FGradCfg<T, K, kFGradMT>::TH;
 }
 
 template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st) {

@@ -111,7 +111,11 @@ template <typename T> struct AdjParams {
 #ifndef PDENET_B2_WARPS
 #define PDENET_B2_WARPS 12
 #endif
+#ifndef PDENET_B2_MT
+#define PDENET_B2_MT 16  // micro-tiles (8 rows each) per large tile: 128-row tiles (64-row tiles: one block barrier per item twice as often, 1.74 vs 1.67 ms)
+#endif
 constexpr int kFGradWarps = PDENET_B2_WARPS;
+constexpr int kFGradMT = PDENET_B2_MT;
 constexpr int kFGradCtasPerSm = kFGradWarps <= 6 ? 2 : 1;
 
 template <typename T> struct FGradParams {

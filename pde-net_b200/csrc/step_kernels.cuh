@@ -21,6 +21,9 @@ template <typename T> struct TransposeCfg {
   static constexpr int ELEMS = 32 * PITCH;
 };
 
+#ifndef PDENET_STEP_SPW
+#define PDENET_STEP_SPW 2   // strips per warp and large tile
+#endif
 template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = NT_;
@@ -32,7 +35,7 @@ template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0> struct Ste
   // warp layout of a tile: WA warps across (32 columns each), WD down, SPW strips of P rows per warp.
   // NT >= 256: the large tile, 64 x (NT/64 * 2P).  NT == 128: the SMALL tile, 32 x 4P (four warps stacked),
   // for problems whose large-tile count would leave SMs idle or badly balanced (BASELINE configs 1 and 3).
-  static constexpr int WA = NT >= 256 ? 2 : 1, WD = NT / 32 / WA, SPW = NT >= 256 ? 2 : 1;
+  static constexpr int WA = NT >= 256 ? 2 : 1, WD = NT / 32 / WA, SPW = NT >= 256 ? PDENET_STEP_SPW : 1;
   static constexpr int TW = 32 * WA, TH = WD * SPW * P;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH = SC;
