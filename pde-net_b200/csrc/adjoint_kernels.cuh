@@ -42,7 +42,7 @@ template <typename T, int K, int NT_ = 256> struct AdjCfg {
 };
 
 template <typename T, int K, int NT_ = 256>
-__global__ void __launch_bounds__(NT_, NT_ == 256 ? 2 : 8) adjoint_kernel(const AdjParams<T> p) {
+__global__ void __launch_bounds__(NT_, NT_ == 512 ? 1 : (NT_ == 256 ? 2 : 8)) adjoint_kernel(const AdjParams<T> p) {
   using Cfg = AdjCfg<T, K, NT_>;
   constexpr int R = Cfg::R, NT = Cfg::NT, VEC = Cfg::VEC, RW = Cfg::RW, TW = Cfg::TW, TH = Cfg::TH;
   constexpr int NV = Cfg::NV, SR = Cfg::SR, SC = Cfg::SC, PITCH = Cfg::PITCH, KK = Cfg::KK;

@@ -382,7 +382,7 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
   p.n_items = B * C * p.tiles_x * p.tiles_y;
   const int vec = 16 / (int)sizeof(T);
   p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
-  const int cap = sms * (small ? 8 : 2); // resident CTAs per SM
+  const int cap = sms * (small ? 8 : (kAdjNT == 512 ? 1 : 2)); // resident CTAs per SM
   const int grid = p.n_items < cap ? p.n_items : cap;
   ProfScope ps(2, st);
   return launch_adjoint<T, K>(p, grid, small, st);

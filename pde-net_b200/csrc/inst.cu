@@ -127,7 +127,7 @@ template <typename T, int K, int NT_> static int launch_adjoint_v(const AdjParam
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 template <typename T, int K> int launch_adjoint(const AdjParams<T> &p, int grid, int small, cudaStream_t st) {
-  return small ? launch_adjoint_v<T, K, 64>(p, grid, st) : launch_adjoint_v<T, K, 256>(p, grid, st);
+  return small ? launch_adjoint_v<T, K, 64>(p, grid, st) : launch_adjoint_v<T, K, kAdjNT>(p, grid, st);
 }
 
 template <typename T, int K, int MT_> static int launch_filter_grad_v(const FGradParams<T> &p, int grid, cudaStream_t st) {
@@ -159,7 +159,7 @@ template <typename T, int K> int upload_taps(int slot, int first, const T *taps,
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
 template <typename T, int K> void adjoint_tile(int small, int &tw, int &th) {
   tw = AdjCfg<T, K>::TW;
-  th = small ? AdjCfg<T, K, 64>::TH : AdjCfg<T, K, 256>::TH;
+  th = small ? AdjCfg<T, K, 64>::TH : AdjCfg<T, K, kAdjNT>::TH;
 }
 
 template int launch_step<PDENET_T, PDENET_K>(int, int, int, int, const StepParams<PDENET_T> &, int, cudaStream_t);

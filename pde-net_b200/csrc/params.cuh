@@ -111,6 +111,10 @@ template <typename T> struct AdjParams {
 #ifndef PDENET_B2_WARPS
 #define PDENET_B2_WARPS 12
 #endif
+#ifndef PDENET_B1_NT
+#define PDENET_B1_NT 256 // threads of the large-tile data-gradient kernel (256: two CTAs per SM; 512: one)
+#endif
+constexpr int kAdjNT = PDENET_B1_NT;
 #ifndef PDENET_B2_MT
 #define PDENET_B2_MT 16  // micro-tiles (8 rows each) per large tile: 128-row tiles (64-row tiles: one block barrier per item twice as often, 1.74 vs 1.67 ms)
 #endif
