@@ -57,8 +57,32 @@ def linear_case(name, k, max_order, B, H, W, steps, dx, dt, seed):
                         grad_coe=lv[3].grad.numpy())
 
 
+def upwind_case(name, k, max_order, C, L, B, H, W, steps, dx, dt, seed):
+    """scheme='upwind' (row f-1): one-sided filters (5e-2 moment noise) so that the twins differ from the filters."""
+    g = torch.Generator().manual_seed(seed)
+    orders = O.order_list(max_order)
+    N = len(orders)
+    M = O.initial_moments(k, orders) + 5e-2 * torch.randn(N, k, k, generator=g, dtype=torch.float64)
+    scales = O.filter_scales(orders, dx)
+    sym = 0.3 * torch.randn(C, O.symnet_param_count(C * N, L), generator=g, dtype=torch.float64)
+    u0 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(steps, B, C, H, W, generator=g, dtype=torch.float64)
+    Mc, sc, uc = M.clone().requires_grad_(True), sym.clone().requires_grad_(True), u0.clone().requires_grad_(True)
+    st = torch.stack(O.upwind_rollout(uc, O.scaled_kernels(Mc, scales), sc, L, dt, steps))
+    (st * w).sum().backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), k=k, max_order=max_order, C=C, L=L, steps=steps, dx=dx,
+                        dt=dt, moments=M.numpy(), scales=scales.numpy(), symnet=sym.numpy(), u0=u0.numpy(),
+                        w=w.numpy(), states=st.detach().numpy(), grad_u0=uc.grad.numpy(),
+                        grad_moments=Mc.grad.numpy(), grad_symnet=sc.grad.numpy())
+
+
 if __name__ == "__main__":
-    rollout_case("rollout_k7_o2_c2_l2", 7, 2, 2, 2, 2, 18, 21, 3, 2 * math.pi / 21, 1e-2, 101)
-    rollout_case("rollout_k5_o2_c1_l3", 5, 2, 1, 3, 2, 9, 14, 2, 0.3, 1e-2, 102)
-    linear_case("linear_k5_o4", 5, 4, 2, 12, 13, 4, 0.2, 1e-3, 103)
+    which = sys.argv[1:] or ["rollout", "linear", "upwind"]
+    if "rollout" in which:
+        rollout_case("rollout_k7_o2_c2_l2", 7, 2, 2, 2, 2, 18, 21, 3, 2 * math.pi / 21, 1e-2, 101)
+        rollout_case("rollout_k5_o2_c1_l3", 5, 2, 1, 3, 2, 9, 14, 2, 0.3, 1e-2, 102)
+    if "linear" in which:
+        linear_case("linear_k5_o4", 5, 4, 2, 12, 13, 4, 0.2, 1e-3, 103)
+    if "upwind" in which:
+        upwind_case("upwind_k5_o2_c2_l2", 5, 2, 2, 2, 2, 13, 17, 3, 0.3, 1e-2, 104)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
