@@ -356,7 +356,7 @@ static int run_step(int mode, int N, int C, int VL, StepParams<T> &p, int B, int
   p.W = W;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  ProfScope ps((mode == MODE_BWD_A || mode == MODE_BWD_A_KEPT || mode == MODE_LIN_BWD_A || mode == MODE_UPW_BWD_A) ? 1
+  ProfScope ps((mode == MODE_BWD_A || mode_is_kept(mode) || mode == MODE_LIN_BWD_A || mode == MODE_UPW_BWD_A) ? 1
                                                                                                                   : 0,
                st);
   return launch_step<T, K>(mode, N, C, VL, p, sms, st);

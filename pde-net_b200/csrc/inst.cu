@@ -27,8 +27,8 @@ static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) 
   p.n_items = p.B * p.tiles_x * p.tiles_y;
   const int slots = sms * (NTO ? kSmallTileCtasPerSm : step_min_blocks<T>(MODE, C * N));
   const int grid = p.n_items < slots ? p.n_items : slots;
-  constexpr bool REV = MODE == MODE_BWD_A || MODE == MODE_BWD_A_KEPT || MODE == MODE_UPW_BWD_A;
-  const size_t smem = Cfg::smem_bytes(p.Psym, REV, MODE == MODE_BWD_A_KEPT);
+  constexpr bool REV = MODE == MODE_BWD_A || mode_is_kept(MODE) || MODE == MODE_UPW_BWD_A;
+  const size_t smem = Cfg::smem_bytes(p.Psym, REV, mode_is_kept(MODE));
   if (smem > kMaxDynamicSmem) return -2; // e.g. 3-channel banks with deep SymNets in the recomputing reverse kernel
   auto kern = step_kernel<T, K, N, C, MODE, VL, LT, NTO>;
   if (allow_smem(kern, smem) != 0) return -4;
@@ -47,12 +47,24 @@ static bool want_small_tiles(int mode, int N, int C, int VL, const StepParams<T>
   return items < (long long)small_tile_factor() * sms;
 }
 
+// kernel A on kept features with x-contiguous strips (MODE_BWD_A_KEPTX): 4 points per thread along x, vector accesses
+template <typename T> static bool keptx_ok(const StepParams<T> &p, int VL) {
+  auto al = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  // fp32 only: measured 0.93 -> 0.82 ms per 32 trajectories there, no gain in fp64 (1.62 ms either way: that kernel is
+  // bound by its shared-memory transposes at 8 warps per SM, not by address arithmetic), where the vertical strips
+  // also keep the SymNet gradient bit-identical to the recomputing path
+  return sizeof(T) == 4 && VL == 16 && p.L == 2 && p.W % 4 == 0 && al(p.feats) && al(p.g) && al(p.lam);
+}
+
 template <typename T, int K>
-int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st) {
-  if (want_small_tiles<T, K>(mode, N, C, VL, p, sms)) {
+int launch_step(int mode_in, int N, int C, int VL, const StepParams<T> &p, int sms, cudaStream_t st) {
+  const int mode = (mode_in == MODE_BWD_A_KEPT && keptx_ok(p, VL)) ? MODE_BWD_A_KEPTX : mode_in;
+  if (want_small_tiles<T, K>(mode_in, N, C, VL, p, sms)) {
     if (mode == MODE_FWD) return launch_step_one<T, K, 6, 2, MODE_FWD, 16, 2, 128>(p, sms, st);
     if (mode == MODE_BWD_A) return launch_step_one<T, K, 6, 2, MODE_BWD_A, 16, 2, 128>(p, sms, st);
     if (mode == MODE_BWD_A_KEPT) return launch_step_one<T, K, 6, 2, MODE_BWD_A_KEPT, 16, 2, 128>(p, sms, st);
+    if constexpr (sizeof(T) == 4)
+      if (mode == MODE_BWD_A_KEPTX) return launch_step_one<T, K, 6, 2, MODE_BWD_A_KEPTX, 16, 2, 128>(p, sms, st);
   }
 #define PDENET_CASE(NN, CC)                                                                                       \
   if (N == NN && C == CC) {                                                                                      \
@@ -68,7 +80,11 @@ int launch_step(int mode, int N, int C, int VL, const StepParams<T> &p, int sms,
         if (VL == 16) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 16>(p, sms, st);                         \
       if (VL == 32) return launch_step_one<T, K, NN, CC, MODE_BWD_A, 32>(p, sms, st);                           \
     }                                                                                                            \
-    if (mode == MODE_BWD_A_KEPT) {                                                                               \
+    if (mode == MODE_BWD_A_KEPTX) {                                                                              \
+      if constexpr (NN * CC + 3 <= 16 && sizeof(T) == 4)                                                         \
+        return launch_step_one<T, K, NN, CC, MODE_BWD_A_KEPTX, 16, 2>(p, sms, st);                               \
+    }                                                                                                            \
+    if (mode == MODE_BWD_A_KEPT || mode == MODE_BWD_A_KEPTX) {                                                   \
       if constexpr (NN * CC + 3 <= 16)                                                                           \
         if (VL == 16 && p.L == 2) return launch_step_one<T, K, NN, CC, MODE_BWD_A_KEPT, 16, 2>(p, sms, st);      \
       if constexpr (NN * CC + 1 < 16)                                                                            \

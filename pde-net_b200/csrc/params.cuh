@@ -15,8 +15,14 @@ enum StepMode {
   // first-order filters, as its last two entries; per output channel and grid point the SymNet sees
   // either a first-order feature or its flipped twin, chosen by the sign of d SymNet / d feature
   MODE_UPW_FWD = 6,
-  MODE_UPW_BWD_A = 7
+  MODE_UPW_BWD_A = 7,
+  // MODE_BWD_A_KEPT with the strip of a thread laid along x (P consecutive points) instead of along y: the kernel
+  // runs no stencils, so nothing needs the vertical strip, and P contiguous values are ONE 16-byte (fp32) or two
+  // (fp64) vector accesses with one address instead of P scalar accesses P rows apart (17 % of kernel A's warp
+  // instructions were 64-bit address arithmetic).  Needs W % P == 0 (and 16-byte aligned planes).
+  MODE_BWD_A_KEPTX = 8
 };
+__host__ __device__ constexpr bool mode_is_kept(int mode) { return mode == MODE_BWD_A_KEPT || mode == MODE_BWD_A_KEPTX; }
 __host__ __device__ constexpr bool mode_is_upwind(int mode) { return mode == MODE_UPW_FWD || mode == MODE_UPW_BWD_A; }
 
 template <typename T> struct StepParams {
@@ -73,13 +79,13 @@ int small_tile_factor();
 #define PDENET_KEPT_F32_BLOCKS 1
 #endif
 template <typename T> __host__ __device__ constexpr int step_p_override(int mode, int M) {
-  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? 4 : 0;
+  return (mode_is_kept(mode) && sizeof(T) == 4 && M <= 12) ? 4 : 0;
 }
 template <typename T> __host__ __device__ constexpr int step_threads_t(int mode, int M) {
-  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_THREADS : step_threads(mode, M);
+  return (mode_is_kept(mode) && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_THREADS : step_threads(mode, M);
 }
 template <typename T> __host__ __device__ constexpr int step_min_blocks(int mode, int M) {
-  return (mode == MODE_BWD_A_KEPT && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_BLOCKS : 1;
+  return (mode_is_kept(mode) && sizeof(T) == 4 && M <= 12) ? PDENET_KEPT_F32_BLOCKS : 1;
 }
 
 template <typename T> struct AdjParams {

@@ -332,7 +332,9 @@ template <int M, int C, int LT> __device__ void build_rev_tables(int Psym, int *
   }
 }
 
-template <typename T, int M, int P, int C, int LT>
+// XC: the P points of the strip are consecutive along x (g is stored with 16-byte vector stores at gp, gp+VEC, ...)
+// instead of P rows apart.
+template <typename T, int M, int P, int C, int LT, bool XC = false>
 __device__ __forceinline__ void symnet_reverse_full(const T (&d)[M][P], const T *syms, int Psym,
                                                     const T (&lam)[C][P], const bool (&valid)[P], T *gp,
                                                     size_t plane, int W, double *sg, T *scratch,
@@ -476,9 +478,29 @@ __device__ __forceinline__ void symnet_reverse_full(const T (&d)[M][P], const T 
             col[(fl * RPF + co * NS + sidx) * TP] = v;
           }
         }
+        if constexpr (XC) {
+          if (valid[0]) {
+            constexpr int VEC = VecOf<T>::N;
 #pragma unroll
-        for (int j = 0; j < P; ++j)
-          if (valid[j]) gp[(size_t)j * W] = gv[j];
+            for (int j = 0; j < P; j += VEC) {
+              typename VecOf<T>::type v;
+              if constexpr (VEC == 2) {
+                v.x = gv[j];
+                v.y = gv[j + 1];
+              } else {
+                v.x = gv[j];
+                v.y = gv[j + 1];
+                v.z = gv[j + 2];
+                v.w = gv[j + 3];
+              }
+              *reinterpret_cast<typename VecOf<T>::type *>(gp + j) = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < P; ++j)
+            if (valid[j]) gp[(size_t)j * W] = gv[j];
+        }
         gp += plane;
       }
     }
@@ -654,7 +676,8 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
-  constexpr bool KEPT = (MODE == MODE_BWD_A_KEPT); // features come from HBM: no tile staging, no block barrier
+  constexpr bool KEPT = mode_is_kept(MODE);       // features come from HBM: no tile staging, no block barrier
+  constexpr bool KX = (MODE == MODE_BWD_A_KEPTX); // ... with the thread's P points consecutive along x
   constexpr bool UPW = mode_is_upwind(MODE);      // bank = NC central filters + the 2 flipped first-order twins
   constexpr bool WITH_GRAD = (MODE == MODE_BWD_A || KEPT || MODE == MODE_UPW_BWD_A);
   constexpr int NC = UPW ? N - 2 : N;             // filters feeding the SymNet per channel
@@ -697,6 +720,7 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
   T *scratch = tiles + region + warp * TransposeCfg<T>::ELEMS; // per-warp transpose scratch (reverse)
   int *rev_tables = reinterpret_cast<int *>(tiles + region + (NT / 32) * TransposeCfg<T>::ELEMS);
   constexpr bool REV_FULL = WITH_GRAD && !UPW && RevFullCfg<M, C, LT>::OK;
+  static_assert(!KX || REV_FULL, "the x-contiguous kept-feature mode exists for the static-depth reverse sweep only");
   if constexpr (REV_FULL) {
     if (tid == 0) build_rev_tables<M, C, (LT >= 0 ? LT : 0)>(Psym, rev_tables, rev_tables + 32);
   }
@@ -717,20 +741,77 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
     const int tx = item % p.tiles_x, t2 = item / p.tiles_x, ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
     const T *tile = tiles + buf * Cfg::TILE_ELEMS;
     const int col = wx * 32 + lane;
-    const int x = tx * TW + col;
 
+    // KX geometry: a strip is RPS rows of the full tile width, lane -> (row lane / LPRW, P columns from (lane % LPRW) * P)
+    constexpr int LPRW = TW / P, RPS = 32 / LPRW;
+    static_assert(!KX || (Cfg::WD * SPW * Cfg::WA * RPS == TH && P % VecOf<T>::N == 0), "KEPTX strip geometry");
 #pragma unroll 1
     for (int s = 0; s < SPW; ++s) {
-      const int row0 = (wy * SPW + s) * P;
-      const int y0 = ty * TH + row0;
-      if (y0 >= H) break; // warp-uniform: the rest of this warp's strips lie below the grid (ragged last tile row)
+      const int row0 = KX ? ((wy * SPW + s) * Cfg::WA + wx) * RPS : (wy * SPW + s) * P;
+      if (ty * TH + row0 >= H) break; // warp-uniform: the rest of this warp's strips lie below the grid (ragged last tile row)
+      const int y0 = ty * TH + row0 + (KX ? lane / LPRW : 0);
+      const int x = KX ? tx * TW + (lane % LPRW) * P : tx * TW + col;
       bool valid[P];
 #pragma unroll
-      for (int j = 0; j < P; ++j) valid[j] = (x < W) && (y0 + j < H);
+      for (int j = 0; j < P; ++j) valid[j] = KX ? ((x < W) && (y0 < H)) : ((x < W) && (y0 + j < H));
       // reverse mode: issue the adjoint loads now so their latency hides behind the stencils
       T lam_raw[WITH_GRAD ? C : 1][P];
       T d[M][P];
-      if constexpr (WITH_GRAD) {
+      if constexpr (KX) {
+        // P contiguous values per plane: vector loads, one address per plane (W % P == 0: a lane is all in or all out)
+        constexpr int VEC = VecOf<T>::N;
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+          const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
+#pragma unroll
+          for (int j = 0; j < P; j += VEC) {
+            if (valid[0]) {
+              ld_vec(lp + j, &lam_raw[co][j]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) lam_raw[co][j + i] = T(0);
+            }
+          }
+        }
+        const T *fp = p.feats + ((size_t)b * M * H + y0) * W + x;
+        const size_t plane = (size_t)H * W;
+#pragma unroll
+        for (int f = 0; f < M; ++f) {
+#pragma unroll
+          for (int j = 0; j < P; j += VEC) {
+            if (valid[0]) {
+              ld_vec(fp + j, &d[f][j]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) d[f][j + i] = T(0);
+            }
+          }
+          fp += plane;
+        }
+        // L1 prefetch of the warp's NEXT strip (possibly in the CTA's next item): RPS rows of TW columns per plane
+        {
+          const int ns = (s + 1 < SPW) ? s + 1 : 0, nit = (s + 1 < SPW) ? item : item + (int)gridDim.x;
+          if (nit < p.n_items) {
+            const int ntx = nit % p.tiles_x, nt2 = nit / p.tiles_x, nty = nt2 % p.tiles_y, nb = nt2 / p.tiles_y;
+            const int nx0 = ntx * TW, ny0 = nty * TH + ((wy * SPW + ns) * Cfg::WA + wx) * RPS;
+            constexpr int LPROW = TW * (int)sizeof(T) / 128;   // 128-byte lines per tile row
+            constexpr int LPP = RPS * LPROW;                   // lines per plane and strip
+            constexpr int NL = (M + C) * LPP;
+#pragma unroll
+            for (int q = 0; q < (NL + 31) / 32; ++q) {
+              const int line = q * 32 + lane, f = line / LPP, rem = line % LPP, row = rem / LPROW;
+              const int hx = (rem % LPROW) * (128 / (int)sizeof(T));
+              if (line < NL && ny0 + row < H && nx0 + hx < W) {
+                const T *src = f < M ? p.feats + (((size_t)nb * M + f) * H + ny0 + row) * W + nx0 + hx
+                                     : p.lam + (((size_t)nb * C + (f - M)) * p.lam_rows + ny0 + row + p.lam_off) * W +
+                                           nx0 + hx;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+              }
+            }
+          }
+        }
+      }
+      if constexpr (WITH_GRAD && !KX) {
 #pragma unroll
         for (int co = 0; co < C; ++co) {
           const T *lp = p.lam + ((size_t)(b * C + co) * p.lam_rows + (y0 + p.lam_off)) * W + x;
@@ -739,7 +820,7 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
         }
       }
       // ---- derivative features of every channel at the strip's P points (rows a5-a6)
-      if constexpr (KEPT) {
+      if constexpr (KEPT && !KX) {
         const T *fp = p.feats + ((size_t)b * M * H + y0) * W + x;
         const size_t plane = (size_t)H * W;
 #pragma unroll
@@ -872,8 +953,8 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
 #pragma unroll
             for (int j = 0; j < P; ++j) lamv[co][j] = p.dt * lam_raw[co][j];
           T *gp = p.g + ((size_t)b * M * p.g_rows + (y0 + p.g_off)) * W + x;
-          symnet_reverse_full<T, M, P, C, (LT >= 0 ? LT : 0)>(d, syms, Psym, lamv, valid, gp, (size_t)p.g_rows * W, W,
-                                                             sg, scratch, rev_tables, rev_tables + 32);
+          symnet_reverse_full<T, M, P, C, (LT >= 0 ? LT : 0), KX>(d, syms, Psym, lamv, valid, gp, (size_t)p.g_rows * W,
+                                                                 W, sg, scratch, rev_tables, rev_tables + 32);
         } else {
           reverse_half<T, M, P, 0, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
           reverse_half<T, M, P, 2, VL, C, LT>(d, syms, Psym, L, valid, lam_raw, p, b, y0, x, sg, scratch);
