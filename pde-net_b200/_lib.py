@@ -140,8 +140,13 @@ def torch_ops():
         if os.environ.get("PDENET_BINDING", "torch").lower() != "ctypes":
             lib()   # builds / verifies both shared objects
             import torch
-            torch.ops.load_library(TORCH_LIB_PATH)
-            _torch_ops = torch.ops.pdenet_b200
+            try:
+                torch.ops.load_library(TORCH_LIB_PATH)
+                _torch_ops = torch.ops.pdenet_b200
+            except OSError as e:   # e.g. a torch build with another C++ ABI: same C-ABI through ctypes instead
+                import warnings
+                warnings.warn("pdenet_b200: the TORCH_LIBRARY shim could not be loaded (%s); using the ctypes binding "
+                              "of the same C-ABI" % e)
     return _torch_ops
 
 

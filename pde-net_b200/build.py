@@ -96,8 +96,23 @@ def _run(cmd):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build both shared objects in place.  Serialised across processes by a file lock: under torchrun every rank
+    may find the binaries stale at the same time, and only one of them may compile."""
     if not force and up_to_date():
         return LIB
+    import fcntl
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():      # another process built it while this one waited
+                return LIB
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
     build_id = source_hash()
