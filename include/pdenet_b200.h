@@ -350,6 +350,40 @@ PDENET_API int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const 
                               double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
                               void *stream);
 
+/* ---- row f-2: PDE-Net 1 SingleNonLinear2d, the whole rollout fused (upstream branch `PDE-Net`,
+ * SingleNonLinear2d.forward [recollection]) -----------------------------------------------------------
+ * u_{t+1} = K0 (*) u_t + dt * ( sum_n coe[n] * (kernels[n] (*) u_t) + f(u_t) ),  coe: N device scalars,
+ * f the piecewise Lagrange interpolant of pdenet_lagrange1d_* (fcoef: mesh*degree+1 node values on [lo, hi]).
+ * One launch per direction on the cluster-resident small-grid path (see pdenet_linear_small_grid_path): it is
+ * available when pdenet_single_nonlinear_fits(...) returns 1 (the 50 x 50 grids the model is used on); for
+ * larger grids the entries return PDENET_E_UNSUPPORTED and the caller steps through
+ * pdenet_linear_rollout_* + pdenet_lagrange1d_* (what pdenet_b200.SingleNonLinear2d does).
+ * Reverse: grad_coe [N], grad_fcoef [mesh*degree+1] (any gradient pointer may be NULL). */
+PDENET_API int pdenet_single_nonlinear_fits(int elem_size, int B, int H, int W, int k, int N);
+PDENET_API int pdenet_single_nonlinear_rollout_fwd_f64(const double *u0, const double *id_kernel, const double *kernels,
+                                            const double *coe, const double *fcoef, double *states, int B, int H, int W,
+                                            int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *stream);
+PDENET_API int pdenet_single_nonlinear_rollout_fwd_f32(const float *u0, const float *id_kernel, const float *kernels,
+                                            const float *coe, const float *fcoef, float *states, int B, int H, int W,
+                                            int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *stream);
+PDENET_API size_t pdenet_single_nonlinear_rollout_bwd_workspace_bytes(int elem_size, int B, int H, int W, int k, int N,
+                                                           int steps, int mesh, int degree);
+PDENET_API int pdenet_single_nonlinear_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states,
+                                            int grad_mode, const double *id_kernel, const double *kernels,
+                                            const double *coe, const double *fcoef, double *grad_u0,
+                                            double *grad_id_kernel, double *grad_kernels, double *grad_coe,
+                                            double *grad_fcoef, void *workspace, size_t workspace_bytes, int B, int H,
+                                            int W, int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *stream);
+PDENET_API int pdenet_single_nonlinear_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states,
+                                            int grad_mode, const float *id_kernel, const float *kernels,
+                                            const float *coe, const float *fcoef, float *grad_u0, float *grad_id_kernel,
+                                            float *grad_kernels, float *grad_coe, float *grad_fcoef, void *workspace,
+                                            size_t workspace_bytes, int B, int H, int W, int k, int N, int steps,
+                                            double dt, double lo, double hi, int mesh, int degree, void *stream);
+
 /* ---- tile policy ---------------------------------------------------------------------------------
  * The step / data-gradient / filter-gradient kernels exist with large tiles (64 x 32..64 points: the headline
  * grids) and with small tiles (32 x 16 / 64 x 16: grids whose large-tile count would leave SMs idle or badly

@@ -8,9 +8,9 @@ from . import _lib, losses, ops, optim, parallel
 from .optim import FlatParams, NumpyFunctionInterface
 from .modules import (FD2d, K2M, LagrangeInterp1d, LagrangeInterpFixInputs2d, M2K, POLYPDE2D, SingleNonLinear2d,
                       VariantCoeLinear2d, order_list, poly)
-from .ops import (fd2d, fd2d_features, fma_peak, k2m, lagrange1d, linear_rollout, m2k, mse_loss, rhs, rollout, slab_step, symnet_eval,
+from .ops import (fd2d, fd2d_features, fma_peak, k2m, lagrange1d, linear_rollout, m2k, mse_loss, rhs, rollout, single_nonlinear_rollout, slab_step, symnet_eval,
                   symnet_param_count)
 
 __all__ = ["losses", "LagrangeInterp1d", "SingleNonLinear2d", "lagrange1d", "LagrangeInterpFixInputs2d", "FlatParams", "NumpyFunctionInterface", "optim", "FD2d", "K2M", "M2K", "POLYPDE2D", "VariantCoeLinear2d", "order_list", "poly", "fd2d",
-           "fd2d_features", "fma_peak", "k2m", "linear_rollout", "m2k", "mse_loss", "rhs", "rollout", "slab_step", "symnet_eval",
+           "fd2d_features", "fma_peak", "k2m", "linear_rollout", "m2k", "mse_loss", "rhs", "rollout", "single_nonlinear_rollout", "slab_step", "symnet_eval",
            "symnet_param_count", "ops", "parallel"]

@@ -47,6 +47,11 @@ _PROTOS = {
     "pdenet_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 6 + [_sz] + [_i] * 9 + [_d, _vp]),
     "pdenet_linear_rollout_fwd_{t}": (_i, [_vp] * 5 + [_i] * 6 + [_d, _vp]),
     "pdenet_linear_small_grid_path": (_i, [_i]),
+    "pdenet_single_nonlinear_fits": (_i, [_i] * 6),
+    "pdenet_single_nonlinear_rollout_fwd_{t}": (_i, [_vp] * 6 + [_i] * 6 + [_d, _d, _d, _i, _i, _vp]),
+    "pdenet_single_nonlinear_rollout_bwd_workspace_bytes": (_sz, [_i] * 9),
+    "pdenet_single_nonlinear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 10 + [_sz] + [_i] * 6
+                                                + [_d, _d, _d, _i, _i, _vp]),
     "pdenet_small_tile_factor": (_i, [_i]),
     "pdenet_linear_rollout_bwd_workspace_bytes": (_sz, [_i] * 6),
     "pdenet_linear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 8 + [_sz] + [_i] * 6 + [_d, _vp]),

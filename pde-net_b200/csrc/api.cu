@@ -1056,7 +1056,8 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
         lin_cluster_dcoe_kernel<T><<<(unsigned)((img + 127) / 128), 128, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
                                                                                   grad_coe);
         if (grad_id_kernel || grad_kernels)
-          lin_cluster_dk_kernel<T><<<dim3(kk, N + 1), 256, 0, st>>>(Rsum, coe, img, kk, (T)dt, grad_id_kernel, grad_kernels);
+          lin_cluster_dk_kernel<T><<<dim3(kk, N + 1), 256, 0, st>>>(Rsum, coe, 0, img, kk, (T)dt, grad_id_kernel,
+                                                                    grad_kernels);
       }
       return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
     }
@@ -1219,6 +1220,106 @@ static int lagrange1d_bwd(const T *x, const T *gy, const T *coef, T *gx, T *gcoe
   }
 #undef PDENET_LAG_CASE
   reduce_flat_kernel<T><<<reduce_blocks(Q), 128, 0, st>>>(partial, blocks, Q, gcoef);
+  return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
+}
+
+// ---- PDE-Net 1 SingleNonLinear2d (row f-2): the whole rollout fused, small grids ------------------
+// u+ = D0*u + dt (sum_n c_n D_n*u + f(u)), constant coefficients c_n, f a piecewise Lagrange polynomial.
+// Runs on the cluster-resident path only (the grids this model is used on: 50 x 50); larger grids return
+// PDENET_E_UNSUPPORTED and the caller steps through pdenet_linear_rollout_* + pdenet_lagrange1d_* instead.
+struct SnlLayout {
+  size_t off_R, off_field, off_lam, off_x, off_part, part_bytes, total;
+};
+static SnlLayout snl_layout(size_t es, int B, int H, int W, int k, int N, int steps, int mesh, int degree, int sms) {
+  SnlLayout l;
+  const size_t img = (size_t)H * W, kk = (size_t)k * k, n = (size_t)steps * B * img;
+  size_t o = 0;
+  l.off_R = o;
+  o = align_up(o + (B + 1) * kk * img * es, 256);
+  l.off_field = o;
+  o = align_up(o + (size_t)N * img * es, 256);
+  l.off_lam = o;
+  o = align_up(o + n * es, 256);
+  l.off_x = o;
+  o = align_up(o + n * es, 256);
+  l.off_part = o;
+  l.part_bytes = (size_t)lagrange_blocks(n, sms) * (mesh * degree + 1) * sizeof(double);
+  o = align_up(o + l.part_bytes, 256);
+  l.total = o;
+  return l;
+}
+
+template <typename T>
+static int snl_fwd(const T *u0, const T *k0, const T *kernels, const T *coe, const T *fcoef, T *states, int B, int H,
+                   int W, int k, int N, int steps, double dt, double lo, double hi, int mesh, int degree, void *stream) {
+  if (!u0 || !k0 || !kernels || !coe || !fcoef || !states || bad_geom(B, 1, H, W, k, N) || steps < 1 || mesh < 1 ||
+      !(hi > lo))
+    return PDENET_E_BADARG;
+  if (degree < 1 || degree > 4) return PDENET_E_UNSUPPORTED;
+  const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sm_count());
+  if (!pl.cs) return PDENET_E_UNSUPPORTED;
+  LinClusterParams<T> q;
+  memset(&q, 0, sizeof(q));
+  q.u0 = u0, q.k0 = k0, q.kernels = kernels, q.coe = coe, q.coe_const = 1, q.states = states;
+  q.fcoef = fcoef, q.f_lo = (T)lo, q.f_inv_h = (T)((double)mesh / (hi - lo)), q.f_mesh = mesh, q.f_deg = degree;
+  q.B = B, q.H = H, q.W = W, q.N = N, q.steps = steps, q.cs = pl.cs, q.hb_max = pl.hb_max;
+  q.dt = (T)dt;
+  ProfScope ps(0, (cudaStream_t)stream);
+  return lin_cluster_fwd_launch<T>(q, k, pl, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int snl_bwd(const T *u0, const T *states, const T *grad_states, int grad_mode, const T *k0, const T *kernels,
+                   const T *coe, const T *fcoef, T *grad_u0, T *grad_k0, T *grad_kernels, T *grad_coe, T *grad_fcoef,
+                   void *workspace, size_t ws_bytes, int B, int H, int W, int k, int N, int steps, double dt, double lo,
+                   double hi, int mesh, int degree, void *stream) {
+  if (!u0 || !grad_states || !k0 || !kernels || !coe || !fcoef || !workspace || bad_geom(B, 1, H, W, k, N) ||
+      steps < 1 || (steps > 1 && !states) || mesh < 1 || !(hi > lo) ||
+      (grad_mode != PDENET_GRAD_LAST && grad_mode != PDENET_GRAD_ALL))
+    return PDENET_E_BADARG;
+  if (degree < 1 || degree > 4) return PDENET_E_UNSUPPORTED;
+  const int sms = sm_count();
+  if (sms <= 0) return PDENET_E_CUDA;
+  const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms);
+  if (!pl.cs) return PDENET_E_UNSUPPORTED;
+  const SnlLayout lay = snl_layout(sizeof(T), B, H, W, k, N, steps, mesh, degree, sms);
+  if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  char *ws = (char *)workspace;
+  const size_t img = (size_t)H * W, stride = (size_t)B * img;
+  const int kk = k * k;
+  T *lam_all = (T *)(ws + lay.off_lam), *x_all = (T *)(ws + lay.off_x), *field = (T *)(ws + lay.off_field);
+  LinClusterParams<T> q;
+  memset(&q, 0, sizeof(q));
+  q.u0 = u0, q.k0 = k0, q.kernels = kernels, q.coe = coe, q.coe_const = 1, q.states = const_cast<T *>(states);
+  q.grad_states = grad_states, q.grad_all = grad_mode == PDENET_GRAD_ALL, q.grad_u0 = grad_u0;
+  q.R = (T *)(ws + lay.off_R);
+  q.fcoef = fcoef, q.f_lo = (T)lo, q.f_inv_h = (T)((double)mesh / (hi - lo)), q.f_mesh = mesh, q.f_deg = degree;
+  q.lam_all = grad_fcoef ? lam_all : nullptr;
+  q.B = B, q.H = H, q.W = W, q.N = N, q.steps = steps, q.cs = pl.cs, q.hb_max = pl.hb_max;
+  q.dt = (T)dt;
+  {
+    ProfScope ps(1, st);
+    if (int rc = lin_cluster_bwd_launch<T>(q, k, pl, st)) return rc;
+  }
+  if (grad_k0 || grad_kernels || grad_coe) {
+    T *Rsum = q.R + (size_t)B * kk * img;
+    ProfScope ps(4, st);
+    lin_cluster_dcoe_kernel<T><<<(unsigned)((img + 127) / 128), 128, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
+                                                                              grad_coe ? field : nullptr);
+    if (grad_coe) lin_cluster_dcoe_const_kernel<T><<<N, 256, 0, st>>>(field, img, grad_coe);
+    if (grad_k0 || grad_kernels)
+      lin_cluster_dk_kernel<T><<<dim3(kk, N + 1), 256, 0, st>>>(Rsum, coe, 1, img, kk, (T)dt, grad_k0, grad_kernels);
+  }
+  if (grad_fcoef) { // node gradient: sum over steps and points of (dt lam_{t+1}) * basis(u_t), one deterministic reduction
+    if (cudaMemcpyAsync(x_all, u0, stride * sizeof(T), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return PDENET_E_CUDA;
+    if (steps > 1 && cudaMemcpyAsync(x_all + stride, states, (size_t)(steps - 1) * stride * sizeof(T),
+                                     cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return PDENET_E_CUDA;
+    if (int rc = lagrange1d_bwd<T>(x_all, lam_all, fcoef, nullptr, grad_fcoef, (size_t)steps * stride, lo, hi, mesh,
+                                   degree, ws + lay.off_part, lay.part_bytes, stream))
+      return rc;
+  }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
 
@@ -1794,6 +1895,51 @@ int pdenet_lagrange1d_bwd_f32(const float *x, const float *gy, const float *coef
                               double lo, double hi, int mesh, int degree, void *workspace, size_t workspace_bytes,
                               void *st) {
   return lagrange1d_bwd<float>(x, gy, coef, gx, gcoef, n, lo, hi, mesh, degree, workspace, workspace_bytes, st);
+}
+
+int pdenet_single_nonlinear_fits(int elem_size, int B, int H, int W, int k, int N) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, 1, H, W, k, N)) return 0;
+  return lin_cluster_plan((size_t)elem_size, B, H, W, k, N, sm_count()).cs ? 1 : 0;
+}
+size_t pdenet_single_nonlinear_rollout_bwd_workspace_bytes(int elem_size, int B, int H, int W, int k, int N, int steps,
+                                                           int mesh, int degree) {
+  if ((elem_size != 4 && elem_size != 8) || bad_geom(B, 1, H, W, k, N) || steps < 1 || mesh < 1 || degree < 1) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  return snl_layout((size_t)elem_size, B, H, W, k, N, steps, mesh, degree, sms).total;
+}
+int pdenet_single_nonlinear_rollout_fwd_f64(const double *u0, const double *id_kernel, const double *kernels,
+                                            const double *coe, const double *fcoef, double *states, int B, int H, int W,
+                                            int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *st) {
+  return snl_fwd<double>(u0, id_kernel, kernels, coe, fcoef, states, B, H, W, k, N, steps, dt, lo, hi, mesh, degree, st);
+}
+int pdenet_single_nonlinear_rollout_fwd_f32(const float *u0, const float *id_kernel, const float *kernels,
+                                            const float *coe, const float *fcoef, float *states, int B, int H, int W,
+                                            int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *st) {
+  return snl_fwd<float>(u0, id_kernel, kernels, coe, fcoef, states, B, H, W, k, N, steps, dt, lo, hi, mesh, degree, st);
+}
+int pdenet_single_nonlinear_rollout_bwd_f64(const double *u0, const double *states, const double *grad_states,
+                                            int grad_mode, const double *id_kernel, const double *kernels,
+                                            const double *coe, const double *fcoef, double *grad_u0,
+                                            double *grad_id_kernel, double *grad_kernels, double *grad_coe,
+                                            double *grad_fcoef, void *workspace, size_t workspace_bytes, int B, int H,
+                                            int W, int k, int N, int steps, double dt, double lo, double hi, int mesh,
+                                            int degree, void *st) {
+  return snl_bwd<double>(u0, states, grad_states, grad_mode, id_kernel, kernels, coe, fcoef, grad_u0, grad_id_kernel,
+                         grad_kernels, grad_coe, grad_fcoef, workspace, workspace_bytes, B, H, W, k, N, steps, dt, lo,
+                         hi, mesh, degree, st);
+}
+int pdenet_single_nonlinear_rollout_bwd_f32(const float *u0, const float *states, const float *grad_states,
+                                            int grad_mode, const float *id_kernel, const float *kernels,
+                                            const float *coe, const float *fcoef, float *grad_u0, float *grad_id_kernel,
+                                            float *grad_kernels, float *grad_coe, float *grad_fcoef, void *workspace,
+                                            size_t workspace_bytes, int B, int H, int W, int k, int N, int steps,
+                                            double dt, double lo, double hi, int mesh, int degree, void *st) {
+  return snl_bwd<float>(u0, states, grad_states, grad_mode, id_kernel, kernels, coe, fcoef, grad_u0, grad_id_kernel,
+                        grad_kernels, grad_coe, grad_fcoef, workspace, workspace_bytes, B, H, W, k, N, steps, dt, lo, hi,
+                        mesh, degree, st);
 }
 
 int pdenet_small_tile_factor(int factor) {

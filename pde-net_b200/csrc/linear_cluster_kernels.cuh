@@ -35,7 +35,38 @@ template <typename T> struct LinClusterParams {
   int B, H, W, N, steps, cs; // cs = CTAs per cluster (= per trajectory)
   int hb_max;        // max rows per band = ceil(H / cs)
   T dt;
+  // PDE-Net 1 SingleNonLinear2d (row f-2): constant coefficients coe[N] instead of fields, and a pointwise source
+  // term dt * f(u), f a piecewise Lagrange polynomial (fcoef[f_mesh * f_deg + 1] node values on [f_lo, f_lo + f_mesh/f_inv_h])
+  int coe_const;
+  const T *fcoef;    // NULL = no source term
+  T f_lo, f_inv_h;
+  int f_mesh, f_deg;
+  T *lam_all;        // reverse, optional: dt * lam_{t+1} of every step, [steps][B][H][W] (feeds the node-gradient reduction)
 };
+
+// value and derivative (w.r.t. x) of the piecewise Lagrange interpolant, run-time degree 1..4
+template <typename T>
+__device__ __forceinline__ void lagrange_eval_rt(T x, const T *coef, T lo, T inv_h, int mesh, int deg, T &f, T &df) {
+  const T sx = (x - lo) * inv_h;
+  int c = (int)floor((double)sx);
+  c = c < 0 ? 0 : (c >= mesh ? mesh - 1 : c);
+  const T t = sx - (T)c;
+  f = T(0);
+  df = T(0);
+  for (int j = 0; j <= deg; ++j) {
+    T v = T(1), dv = T(0);
+    for (int m = 0; m <= deg; ++m) {
+      if (m == j) continue;
+      const T inv = T(deg) / T(j - m), fac = (t - T(m) / T(deg)) * inv;
+      dv = dv * fac + v * inv;
+      v *= fac;
+    }
+    const T cj = coef[c * deg + j];
+    f = fma_(cj, v, f);
+    df = fma_(cj, dv, df);
+  }
+  df *= inv_h;
+}
 
 // rows [y0, y1) of cluster rank c
 __device__ __forceinline__ int band_start(int c, int H, int cs) { return (int)(((long long)c * H) / cs); }
@@ -61,7 +92,7 @@ __device__ __forceinline__ void build_combined_stencil(const LinClusterParams<T>
 #pragma unroll
     for (int e = 0; e < KK; ++e) acc[e] = T(0);
     for (int n = 0; n < N; ++n) {
-      const T c = p.coe[((size_t)n * H + g) * W + x];
+      const T c = p.coe_const ? p.coe[n] : p.coe[((size_t)n * H + g) * W + x];
       const T *kn = taps + (n + 1) * KK;
 #pragma unroll
       for (int e = 0; e < KK; ++e) acc[e] = fma_(c, kn[e], acc[e]);
@@ -136,6 +167,11 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_fwd_kern
         const T *ur = cur + (py[q] + a) * W;
 #pragma unroll
         for (int bb = 0; bb < K; ++bb) acc = fma_(wp[(size_t)(a * K + bb) * W], ur[xm[q][bb]], acc);
+      }
+      if (p.fcoef) {
+        T fv, dfv;
+        lagrange_eval_rt(cur[(R + py[q]) * W + px[q]], p.fcoef, p.f_lo, p.f_inv_h, p.f_mesh, p.f_deg, fv, dfv);
+        acc = fma_(p.dt, fv, acc);
       }
       nxt[(R + py[q]) * W + px[q]] = acc;
       out[py[q] * W + px[q]] = acc;
@@ -222,6 +258,12 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_bwd_kern
           acc = fma_(wr[(size_t)bb * W + sx], lr[sx], acc);
         }
       }
+      if (p.fcoef) { // source term: lam_t += dt f'(u_t) lam_{t+1}; its node gradient is reduced from lam_all afterwards
+        T fv, dfv;
+        lagrange_eval_rt(ubuf[(R + py[q]) * W + px[q]], p.fcoef, p.f_lo, p.f_inv_h, p.f_mesh, p.f_deg, fv, dfv);
+        acc = fma_(p.dt * dfv, lp, acc);
+        if (p.lam_all) p.lam_all[(size_t)t * stride + (size_t)b * img + (size_t)(y0 + py[q]) * W + px[q]] = p.dt * lp;
+      }
       if (inj) acc += inj[py[q] * W + px[q]];
       nxt[(R + py[q]) * W + px[q]] = acc;
       if (gu) gu[py[q] * W + px[q]] = acc;
@@ -265,15 +307,32 @@ __global__ void lin_cluster_dcoe_kernel(const T *R, int B, int KK, size_t img, c
       grad_coe[(size_t)n * img + pidx] = (T)((double)dt * s);
     }
 }
+// constant coefficients: grad_coe[n] = sum_p field_grad[n][p]  (one block per n, fixed order)
+template <typename T> __global__ void __launch_bounds__(256) lin_cluster_dcoe_const_kernel(const T *field, size_t img, T *out) {
+  const T *r = field + (size_t)blockIdx.x * img;
+  double s = 0.0;
+  for (size_t i = threadIdx.x; i < img; i += blockDim.x) s += (double)r[i];
+  __shared__ double red[8];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    out[blockIdx.x] = (T)tot;
+  }
+}
 // block (n, e): n = 0 -> dK0[e] = sum_p Rsum[e][p];  n >= 1 -> dK_n[e] = dt * sum_p coe[n-1][p] * Rsum[e][p]
 template <typename T>
-__global__ void __launch_bounds__(256) lin_cluster_dk_kernel(const T *Rsum, const T *coe, size_t img, int KK, T dt,
-                                                             T *grad_k0, T *grad_kernels) {
+__global__ void __launch_bounds__(256) lin_cluster_dk_kernel(const T *Rsum, const T *coe, int coe_const, size_t img, int KK,
+                                                             T dt, T *grad_k0, T *grad_kernels) {
   const int n = blockIdx.y, e = blockIdx.x;
   const T *r = Rsum + (size_t)e * img;
-  const T *c = n > 0 ? coe + (size_t)(n - 1) * img : nullptr;
+  const T *c = (n > 0 && !coe_const) ? coe + (size_t)(n - 1) * img : nullptr;
+  const double cc = (n > 0 && coe_const) ? (double)coe[n - 1] : 1.0;
   double s = 0.0;
-  for (size_t i = threadIdx.x; i < img; i += blockDim.x) s += (c ? (double)c[i] : 1.0) * (double)r[i];
+  for (size_t i = threadIdx.x; i < img; i += blockDim.x) s += (c ? (double)c[i] : cc) * (double)r[i];
   __shared__ double red[8];
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);

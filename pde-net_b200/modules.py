@@ -399,9 +399,9 @@ class SingleNonLinear2d(nn.Module):
     ``u+ = D0*u + dt * (sum_n c_n (D_n*u) + f(u))`` with learnable filters, one learnable constant
     coefficient c_n per derivative term and ``f`` a learnable piecewise Lagrange polynomial.
 
-    Each step is one fused linear step (``ops.linear_rollout`` with the constants broadcast to
-    fields) plus the interpolation op; unlike the two headline models the steps of a rollout are
-    not fused into one call yet (the source term sits between them)."""
+    On the grids the model is used on (50 x 50: whatever fits the cluster-resident small-grid path) the whole
+    rollout is ONE fused op per direction (``ops.single_nonlinear_rollout``); larger grids step through the fused
+    linear step (``ops.linear_rollout`` with the constants broadcast to fields) plus the interpolation op."""
 
     def __init__(self, kernel_size, max_order, dx, dt, constraint="moment", nonlinear_interp_degree=2,
                  nonlinear_interp_mesh_bound=(-15.0, 15.0), nonlinear_interp_mesh_size=20, dtype=torch.float64):
@@ -432,12 +432,20 @@ class SingleNonLinear2d(nn.Module):
     def coe_params(self):
         return iter([self.coe, self.nonlinearfitter.interp_coe])
 
-    def forward(self, init: torch.Tensor, stepnum: int) -> torch.Tensor:
+    def forward(self, init: torch.Tensor, stepnum: int, fused=None) -> torch.Tensor:
+        """``fused=None``: the whole rollout as ONE op (``ops.single_nonlinear_rollout``: one launch per direction,
+        trajectory resident in shared memory) when the grid fits the small-grid path, else a per-step loop of the
+        fused linear step + the interpolation op (larger grids)."""
         ks = self.scaled_kernels()
         B, H, W = init.shape
+        nf = self.nonlinearfitter
+        if fused is None:
+            fused = ops.single_nonlinear_fits(init, ks[1:])
+        if fused:
+            return ops.single_nonlinear_rollout(init, ks[0], ks[1:], self.coe, nf.interp_coe, self.dt, int(stepnum),
+                                                nf.mesh_bound[0], nf.mesh_bound[1], nf.mesh_size, nf.degree)
         fields = self.coe[:, None, None].expand(-1, H, W).contiguous()
         u = init
         for _ in range(int(stepnum)):
-            u = ops.linear_rollout(u, ks[0], ks[1:], fields, self.dt, 1, last_only=True) \
-                + self.dt * self.nonlinearfitter(u)
+            u = ops.linear_rollout(u, ks[0], ks[1:], fields, self.dt, 1, last_only=True) + self.dt * nf(u)
         return u

@@ -515,6 +515,62 @@ def lagrange1d(x: torch.Tensor, coef: torch.Tensor, lo: float, hi: float, mesh: 
     return _Lagrange1d.apply(x, coef, float(lo), float(hi), int(mesh), int(degree))
 
 
+class _SingleNonlinearRollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u0, id_kernel, kernels, coe, fcoef, dt, steps, lo, hi, mesh, degree):
+        u0 = _req(u0, "u0")
+        id_kernel, kernels = _req(id_kernel, "id_kernel", u0.dtype), _req(kernels, "kernels", u0.dtype)
+        coe, fcoef = _req(coe, "coe", u0.dtype), _req(fcoef, "fcoef", u0.dtype)
+        B, H, W = u0.shape
+        N, k, _ = kernels.shape
+        if coe.numel() != N or fcoef.numel() != mesh * degree + 1:
+            raise ValueError("coe must hold N constants and fcoef mesh*degree + 1 node values")
+        states = torch.empty(steps, B, H, W, dtype=u0.dtype, device=u0.device)
+        _lib.check(_lib.fn("pdenet_single_nonlinear_rollout_fwd", u0.dtype)(
+            _ptr(u0), _ptr(id_kernel), _ptr(kernels), _ptr(coe), _ptr(fcoef), _ptr(states), B, H, W, k, N, steps,
+            float(dt), lo, hi, mesh, degree, _stream()), "pdenet_single_nonlinear_rollout_fwd")
+        ctx.save_for_backward(u0, id_kernel, kernels, coe, fcoef)
+        ctx.states = states
+        ctx.cfg = (float(dt), steps, lo, hi, mesh, degree)
+        return states[-1]
+
+    @staticmethod
+    def backward(ctx, grad):
+        u0, id_kernel, kernels, coe, fcoef = ctx.saved_tensors
+        dt, steps, lo, hi, mesh, degree = ctx.cfg
+        B, H, W = u0.shape
+        N, k, _ = kernels.shape
+        grad = _req(grad, "grad_state", u0.dtype)
+        nbytes = _lib.lib().pdenet_single_nonlinear_rollout_bwd_workspace_bytes(u0.element_size(), B, H, W, k, N, steps,
+                                                                                mesh, degree)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=u0.device)
+        need = ctx.needs_input_grad
+        outs = [torch.empty_like(t) if n else None for t, n in zip((u0, id_kernel, kernels, coe, fcoef), need[:5])]
+        _lib.check(_lib.fn("pdenet_single_nonlinear_rollout_bwd", u0.dtype)(
+            _ptr(u0), _ptr(ctx.states), _ptr(grad), _lib.GRAD_LAST, _ptr(id_kernel), _ptr(kernels), _ptr(coe), _ptr(fcoef),
+            *[_ptr(o) for o in outs], _ptr(ws), nbytes, B, H, W, k, N, steps, dt, lo, hi, mesh, degree, _stream()),
+            "pdenet_single_nonlinear_rollout_bwd")
+        return tuple(outs) + (None,) * 6
+
+
+def single_nonlinear_fits(u0: torch.Tensor, kernels: torch.Tensor) -> bool:
+    """True if the fused SingleNonLinear2d rollout (cluster-resident small-grid path) serves this shape."""
+    B, H, W = u0.shape
+    N, k, _ = kernels.shape
+    return _lib.lib().pdenet_single_nonlinear_fits(u0.element_size(), B, H, W, k, N) == 1
+
+
+def single_nonlinear_rollout(u0, id_kernel, kernels, coe, fcoef, dt: float, steps: int, lo: float, hi: float, mesh: int,
+                             degree: int) -> torch.Tensor:
+    """PDE-Net 1 ``SingleNonLinear2d`` rollout ``u <- K0*u + dt*(sum_n coe_n (K_n*u) + f(u))`` as ONE fused op (row
+    f-2): final state after ``steps`` blocks, differentiable w.r.t. everything.  Small grids only
+    (:func:`single_nonlinear_fits`); ``coe`` [N] constants, ``fcoef`` the node values of ``f``."""
+    if steps < 1:
+        raise ValueError("steps must be >= 1")
+    return _SingleNonlinearRollout.apply(u0, id_kernel, kernels, coe, fcoef, float(dt), int(steps), float(lo), float(hi),
+                                         int(mesh), int(degree))
+
+
 class _MseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, states, observed, weights):

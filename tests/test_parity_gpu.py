@@ -993,6 +993,62 @@ def test_lagrange1d_matches_oracle(P, cuda_device, degree, dtype):
     assert rel(yn, coef) < (1e-12 if dtype == torch.float64 else 1e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_single_nonlinear_fused_rollout(P, cuda_device, dtype):
+    """SingleNonLinear2d as ONE fused op per direction (cluster-resident small-grid path with the source term and
+    constant coefficients) == the per-step loop == the oracle: state and the gradients of everything (filters,
+    constants, node values of f, input)."""
+    dev = cuda_device
+    k, max_order, B, H, W, steps = 5, 2, 4, 50, 50, 6
+    dx, dt = 2 * math.pi / W, 2e-3
+    model = P.SingleNonLinear2d(k, max_order, dx, dt, nonlinear_interp_degree=2, nonlinear_interp_mesh_bound=(-1.5, 1.5),
+                                nonlinear_interp_mesh_size=6, dtype=dtype).to(dev)
+    g = torch.Generator().manual_seed(79)
+    with torch.no_grad():
+        for fd in [model.id] + model.fds:
+            # (the order-(0,0) filter D0 is not multiplied by dt: noise in its high moments is a grid-scale amplification
+            # per step, 1e-2 there turns rounding noise into 1e-4 within six steps of single precision)
+            amp = 1e-4 if fd is model.id else 1e-2
+            fd.moment.add_(amp * torch.randn(fd.moment.shape, generator=g, dtype=torch.float64).to(dev, dtype))
+            fd.x_proj()
+        model.coe.copy_((0.3 * dx ** 2 * torch.randn(model.coe.shape, generator=g, dtype=torch.float64)).to(dtype))
+        model.nonlinearfitter.interp_coe.copy_(torch.sin(model.nonlinearfitter.nodes() * 2))
+    u0 = smooth_field(B, 1, H, W, 80)[:, 0]
+    w = torch.randn(u0.shape, generator=g, dtype=torch.float64)
+    params = [model.coe, model.nonlinearfitter.interp_coe] + [fd.moment for fd in [model.id] + model.fds]
+    res = {}
+    for fused in (True, False):
+        for prm in params:
+            prm.grad = None
+        ud = u0.to(dev, dtype).requires_grad_(True)
+        out = model(ud, steps, fused=fused)
+        (out * w.to(dev, dtype)).sum().backward()
+        res[fused] = [out.detach(), ud.grad] + [prm.grad.clone() for prm in params]
+    assert P.ops.single_nonlinear_fits(u0.to(dev, dtype), model.scaled_kernels()[1:])
+    # oracle
+    ks = model.scaled_kernels().detach().double().cpu()
+    K0, Ks = ks[0].clone().requires_grad_(True), ks[1:].clone().requires_grad_(True)
+    coe = model.coe.detach().double().cpu().clone().requires_grad_(True)
+    fc = model.nonlinearfitter.interp_coe.detach().double().cpu().clone().requires_grad_(True)
+    uc = u0.clone().requires_grad_(True)
+    u = uc
+    for _ in range(steps):
+        u = O.single_nonlinear_step(u, K0, Ks, coe, fc, -1.5, 1.5, 6, 2, dt)
+    (u * w).sum().backward()
+    if dtype == torch.float64:
+        for i, (a, b) in enumerate(zip(res[True], res[False])):
+            # moment gradients (i >= 4) pass through A^-T dK A^-1, which amplifies the re-association difference
+            assert rel(a, b) < (1e-11 if i < 4 else 1e-9), i
+        assert rel(res[True][0], u) < 1e-11
+        assert rel(res[True][1], uc.grad) < 1e-10
+        assert rel(res[True][2], coe.grad) < 1e-9
+        assert rel(res[True][3], fc.grad) < 1e-9
+    else:
+        assert rel(res[True][0], u) < 1e-5 * steps
+        assert rel(res[True][3], fc.grad) < 1e-4
+        assert rel(res[True][0], res[False][0]) < 1e-5 * steps
+
+
 def test_single_nonlinear_module_matches_oracle(P, cuda_device):
     """PDE-Net 1 model with the interpolated nonlinear source term (u_t = c lap(u) + f(u) shape)."""
     dev = cuda_device
