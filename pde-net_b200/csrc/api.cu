@@ -68,6 +68,7 @@ struct ProfScope {
   extern template int launch_step<TT, KK>(int, int, int, int, const StepParams<TT> &, int, cudaStream_t);        \
   extern template int launch_adjoint<TT, KK>(const AdjParams<TT> &, int, int, cudaStream_t);                     \
   extern template int upload_taps<TT, KK>(int, int, const TT *, int, cudaStream_t);                              \
+  extern template int upload_raw<TT, KK>(int, size_t, const void *, size_t, cudaStream_t);                       \
   extern template size_t step_smem_bytes<TT, KK>(int, int, int, int);                                            \
   extern template int launch_filter_grad<TT, KK>(const FGradParams<TT> &, int, int, cudaStream_t);               \
   extern template void filter_grad_tile<TT, KK>(int, int &, int &);                                              \
@@ -291,6 +292,50 @@ static int sandwich(int which, const T *in, const double *scale_host, const unsi
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32: second, filter-innermost copy of the bank (pairs of filters for the packed FFMA2 of the step kernels),
+// built from the same sources in a per-slot device scratch and copied into the second half of the slot.
+// Bank = [k0 (optional)] + n filters of `taps` + [2 twins (optional)].
+__device__ __align__(16) unsigned char g_pair_scratch[kConstSlots][kPairedBytes];
+
+__global__ void pack_pairs_kernel(const float *k0, const float *taps, int n, const float *twins, int kk, float *out) {
+  const int nbank = (k0 ? 1 : 0) + n + (twins ? 2 : 0), np2 = (nbank + 1) / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kk * np2 * 2) return;
+  const int h = idx & 1, np = (idx >> 1) % np2, e = (idx >> 1) / np2, f = 2 * np + h;
+  float v = 0.f;
+  if (f < nbank) {
+    int g = f;
+    if (k0) {
+      if (g == 0) {
+        v = k0[e];
+        g = -1;
+      } else {
+        g -= 1;
+      }
+    }
+    if (g >= 0) v = g < n ? taps[g * kk + e] : twins[(g - n) * kk + e];
+  }
+  out[idx] = v;
+}
+
+template <typename T>
+static int upload_pairs(const SlotLease &lease, const T *k0, const T *taps, int n, const T *twins, int k, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    void *scr = nullptr;
+    if (cudaGetSymbolAddress(&scr, g_pair_scratch) != cudaSuccess) return PDENET_E_CUDA;
+    float *out = (float *)((unsigned char *)scr + (size_t)lease.slot * kPairedBytes);
+    const int nbank = (k0 ? 1 : 0) + n + (twins ? 2 : 0), cnt = k * k * ((nbank + 1) / 2) * 2;
+    if ((size_t)cnt * sizeof(float) > (size_t)kPairedBytes) return PDENET_E_UNSUPPORTED;
+    pack_pairs_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(k0, taps, n, twins, k * k, out);
+    if (cudaGetLastError() != cudaSuccess) return PDENET_E_CUDA;
+    int rc = 0;
+    PDENET_DISPATCH_K(k, rc = (upload_raw<T, KK_>(lease.slot, kPairedBytes, out, (size_t)cnt * sizeof(float), st)));
+    return rc;
+  } else {
+    return 0;
+  }
+}
+
 // upload [n][k][k] taps (optionally preceded by one extra filter k0) into a leased constant slot
 template <typename T>
 static int upload(const SlotLease &lease, const T *k0, const T *taps, int n, int k, cudaStream_t st) {
@@ -302,7 +347,8 @@ static int upload(const SlotLease &lease, const T *k0, const T *taps, int n, int
     first = 1;
   }
   PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, first, taps, n, st)));
-  return rc;
+  if (rc) return rc;
+  return upload_pairs<T>(lease, k0, taps, n, nullptr, k, st);
 }
 
 // ---- pseudo-upwind bank (row f-1): bank order puts order (0,1) at index 1 (derivative along W) and
@@ -342,7 +388,8 @@ static int upload_upwind(const SlotLease &lease, const T *kernels, int N, int k,
   PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, 0, kernels, N, st)));
   if (rc) return rc;
   PDENET_DISPATCH_K(k, rc = (upload_taps<T, KK_>(lease.slot, N, twins, 2, st)));
-  return rc;
+  if (rc) return rc;
+  return upload_pairs<T>(lease, nullptr, kernels, N, twins, k, st);
 }
 
 static bool bad_geom(int B, int C, int H, int W, int k, int N) {

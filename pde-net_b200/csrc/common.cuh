@@ -21,7 +21,25 @@ __constant__ __align__(16) unsigned char c_slots[kConstSlots * kConstSlotBytes];
 template <typename T> __device__ __forceinline__ const T *const_taps(int slot) {
   return reinterpret_cast<const T *>(c_slots + slot * kConstSlotBytes);
 }
+// fp32 only: the second half of a slot holds the bank a second time, FILTER-innermost and padded to an even filter
+// count -- [K*K taps][NP2 pairs][2] -- so that the taps of two filters are one 64-bit uniform load and feed one
+// packed FFMA2 (see step_kernels.cuh)
+__device__ __forceinline__ const float2 *const_taps_paired(int slot) {
+  return reinterpret_cast<const float2 *>(c_slots + slot * kConstSlotBytes + kConstSlotBytes / 2);
+}
 #endif
+constexpr int kPairedBytes = kConstSlotBytes / 2;
+
+// packed single-precision FMA (SASS FFMA2): d = (x * w.x + c.x, x * w.y + c.y).  The broadcast of x and a
+// uniform-register pair for w are folded into the instruction by ptxas (`FFMA2 R, R.F32, UR.F32x2.HI_LO, R`).
+__device__ __forceinline__ float2 ffma2_bcast(float x, float2 w, float2 c) {
+  float2 d;
+  asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %2};\n mov.b64 rb, {%3, %4};\n mov.b64 rc, {%5, %6};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(x), "f"(w.x), "f"(w.y), "f"(c.x), "f"(c.y));
+  return d;
+}
 
 // 16-byte vector type per scalar type (LDS.128 / STG.128 granularity).
 template <typename T> struct VecOf;

@@ -172,6 +172,15 @@ template <typename T, int K> int upload_taps(int slot, int first, const T *taps,
   return e == cudaSuccess ? 0 : -4;
 }
 
+// raw stream-ordered copy into a constant slot at a byte offset (the filter-innermost fp32 copy of the bank)
+template <typename T, int K> int upload_raw(int slot, size_t offset, const void *src, size_t bytes, cudaStream_t st) {
+  if (slot < 0 || slot >= kConstSlots || offset + bytes > (size_t)kConstSlotBytes) return -2;
+  return cudaMemcpyToSymbolAsync(c_slots, src, bytes, (size_t)slot * kConstSlotBytes + offset, cudaMemcpyDeviceToDevice,
+                                 st) == cudaSuccess
+             ? 0
+             : -4;
+}
+
 template <typename T, int K> int adjoint_vlb() { return AdjCfg<T, K>::VLB; }
 template <typename T, int K> void adjoint_tile(int small, int &tw, int &th) {
   tw = AdjCfg<T, K>::TW;
@@ -185,6 +194,7 @@ template int launch_filter_grad<PDENET_T, PDENET_K>(const FGradParams<PDENET_T> 
 template void filter_grad_tile<PDENET_T, PDENET_K>(int, int &, int &);
 template int adjoint_vlb<PDENET_T, PDENET_K>();
 template int upload_taps<PDENET_T, PDENET_K>(int, int, const PDENET_T *, int, cudaStream_t);
+template int upload_raw<PDENET_T, PDENET_K>(int, size_t, const void *, size_t, cudaStream_t);
 template void adjoint_tile<PDENET_T, PDENET_K>(int, int &, int &);
 
 } // namespace pdenet

@@ -25,6 +25,7 @@ template <typename T, int K> void filter_grad_tile(int small, int &tw, int &th);
 template <typename T, int K> int adjoint_vlb();
 // copy n_filters [K][K] filters (device memory) into constant slot `slot`, starting at filter index `first`
 template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st);
+template <typename T, int K> int upload_raw(int slot, size_t offset, const void *src, size_t bytes, cudaStream_t st);
 template <typename T, int K> void adjoint_tile(int small, int &tw, int &th);
 
 } // namespace pdenet

@@ -857,6 +857,37 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
       for (int c = 0; c < (KEPT ? 0 : C); ++c) {
         const T *ut = tile + (c * SR + row0) * PITCH + col;
         T acc[N][P];
+        if constexpr (sizeof(T) == 4) {
+          // fp32: two filters per packed FMA (FFMA2).  The taps of filters (2np, 2np+1) are one 64-bit uniform load
+          // from the filter-innermost copy of the bank, the window value is broadcast inside the instruction: half
+          // the FMA issue slots of the scalar loop for the same, bit-identical arithmetic (the fp32 kernels are
+          // issue-bound).
+          constexpr int NP2 = (N + 1) / 2;
+          const float2 *cw2 = const_taps_paired(p.slot);
+          float2 acc2[NP2][P];
+#pragma unroll
+          for (int np = 0; np < NP2; ++np)
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc2[np][j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int bb = 0; bb < K; ++bb) {
+            float win[P + K - 1];
+#pragma unroll
+            for (int i = 0; i < P + K - 1; ++i) win[i] = ut[i * PITCH + bb];
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+#pragma unroll
+              for (int np = 0; np < NP2; ++np) {
+                const float2 w2 = cw2[(a * K + bb) * NP2 + np]; // warp-uniform -> LDCU.64 + uniform-register pair
+#pragma unroll
+                for (int j = 0; j < P; ++j) acc2[np][j] = ffma2_bcast(win[j + a], w2, acc2[np][j]);
+              }
+          }
+#pragma unroll
+          for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[n][j] = (n & 1) ? acc2[n / 2][j].y : acc2[n / 2][j].x;
+        } else {
 #pragma unroll
         for (int n = 0; n < N; ++n)
 #pragma unroll
@@ -874,6 +905,7 @@ __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO
 #pragma unroll
               for (int j = 0; j < P; ++j) acc[n][j] = fma_(win[j + a], w, acc[n][j]);
             }
+        }
         }
 #pragma unroll
         for (int n = 0; n < N; ++n)
