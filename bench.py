@@ -443,8 +443,8 @@ def slab_record(P, dev, rank, world, args):
         mine = synth_fields(0, 1, C, H, W, dev, dtype)[:, :, slab.row0:slab.row0 + slab.Hs].contiguous()
         n_total = C * H * W
 
-        def seed(f):  # loss = mean square of the final state over the WHOLE grid
-            return 2.0 * f / n_total
+        def seed(f, out=None):  # loss = mean square of the final state over the WHOLE grid
+            return torch.mul(f, 2.0 / n_total, out=out)
 
         how = "fused peer stores (symmetric memory over NVLink), features kept"
         pb = None

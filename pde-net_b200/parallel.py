@@ -231,20 +231,44 @@ class SlabPeerBuffers:
         if self.hdl is not None:
             self.hdl.barrier()
 
+    def _peer_view(self, peer: int, elem_off: int, shape):
+        return self.hdl.get_buffer(peer, tuple(shape), self.flat.dtype, elem_off)
+
+    def fill_ghosts(self, which: str, i: int, halo: int) -> None:
+        """Ghost fill of ``state[i]`` / ``lam[i]`` without NCCL: store my first / last ``halo`` owned rows straight
+        into the ring neighbours' ghost rows of the same buffer (peer copies over NVLink).  The caller brackets it
+        with ``barrier()``: one before (the neighbours are done with the buffer), one after (their rows have
+        landed in mine)."""
+        slab, Hs = self.slab, self.slab.Hs
+        ext = (self.state if which == "state" else self.lam)[i]
+        base = i * self.n_state if which == "state" else self._lam_off + i * self.n_lam
+        top_rows, bot_rows = ext[:, :, halo:2 * halo], ext[:, :, Hs:Hs + halo]
+        if self.hdl is None:
+            ext[:, :, :halo] = bot_rows
+            ext[:, :, halo + Hs:] = top_rows
+            return
+        up = self._peer_view(slab.up, base, ext.shape)
+        dn = self._peer_view(slab.down, base, ext.shape)
+        up[:, :, halo + Hs:].copy_(top_rows)      # my first rows -> `up`'s bottom ghosts
+        dn[:, :, :halo].copy_(bot_rows)           # my last rows  -> `down`'s top ghosts
+
 
 def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u_local: torch.Tensor,
                              kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
                              grad_last_local: Callable, keep_features: Optional[bool] = None):
     """``SlabDecomposition.rollout_fwd_bwd`` with the halo exchanges fused into the step kernels
-    (peer stores into the neighbours' ghost rows, `SlabPeerBuffers`).  Only the initial state and
-    the loss seed need a conventional ghost fill."""
+    (peer stores into the neighbours' ghost rows, `SlabPeerBuffers`).  The initial state and the loss
+    seed fill the neighbours' ghost rows with peer copies (`SlabPeerBuffers.fill_ghosts`): no NCCL
+    point-to-point on the path.  ``grad_last_local`` may accept ``out=`` (a strided view of the adjoint
+    buffer) to write the seed in place."""
     from . import ops
     h, h2, Hs = slab.halo, 2 * slab.halo, slab.Hs
     B, C, _, W = u_local.shape
     feats = _slab_feature_buffers(keep_features, steps, B, C, kernels.shape[0], Hs, W, u_local)
     bufs.state[0][:, :, h2:h2 + Hs] = u_local
-    slab.exchange(bufs.state[0], h2)
-    bufs.barrier()                                   # every rank's buffers are ready to be written
+    bufs.barrier()                                   # every rank is done with the buffers of its previous pass
+    bufs.fill_ghosts("state", 0, h2)
+    bufs.barrier()                                   # the neighbours' rows have landed
     for t in range(steps):
         up, dn = bufs.state_peers(t + 1)
         ops.slab_step(bufs.state[t], kernels, symnet, L, dt, h2, bufs.state[t + 1], h2, up, dn, h2,
@@ -252,8 +276,15 @@ def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u
         bufs.barrier()                               # neighbours' boundary rows have landed
     final = bufs.state[steps][:, :, h2:h2 + Hs].contiguous()
     cur = 0
-    bufs.lam[cur][:, :, h:h + Hs] = grad_last_local(final)
-    slab.exchange(bufs.lam[cur], h)
+    seed_view = bufs.lam[cur][:, :, h:h + Hs]
+    try:
+        seed = grad_last_local(final, out=seed_view)
+    except TypeError:                                # a plain callable: one more slab-sized copy
+        seed = grad_last_local(final)
+    if seed is not seed_view:
+        seed_view.copy_(seed)
+    bufs.fill_ghosts("lam", cur, h)                  # lam[cur] was last written two steps before the previous
+    bufs.barrier()                                   # pass ended: every rank is past reading it
     bwd = ops.SlabBackward(kernels, symnet, L, dt, B, C, Hs, W)
     for t in range(steps - 1, -1, -1):
         up, dn = bufs.lam_peers(cur ^ 1)
