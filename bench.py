@@ -451,8 +451,11 @@ def slab_record(P, dev, rank, world, args):
         try:
             pb = PP.SlabPeerBuffers(slab, 1, C, W, blocks, dtype, dev)
 
+            pb.input_view().copy_(mine)      # the slab lives in the symmetric buffer: used in place every pass
+
             def run():
-                return PP.slab_rollout_fwd_bwd_p2p(slab, pb, mine, Ks, sym, L, dt, blocks, seed, keep_features=True)
+                return PP.slab_rollout_fwd_bwd_p2p(slab, pb, pb.input_view(), Ks, sym, L, dt, blocks, seed,
+                                                   keep_features=True, copy_outputs=False)
             fin, gu, gk, gs = run()
         except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable: NCCL send/recv halos
             how = "NCCL send/recv halo exchange, features kept (symmetric memory unavailable: %s)" % type(e).__name__
@@ -469,16 +472,16 @@ def slab_record(P, dev, rank, world, args):
         if rank == 0:
             u_full = synth_fields(0, 1, C, H, W, dev, dtype)
 
+            ud, Kd, sd = [t.detach().clone().requires_grad_(True) for t in (u_full, Ks, sym)]
+
             def single():
-                ud, Kd, sd = [t.detach().clone().requires_grad_(True) for t in (u_full, Ks, sym)]
                 o = P.rollout(ud, Kd, sd, L, dt, blocks, last_only=True, batch_chunk=1)
-                o.square().mean().backward()
-                return o.detach(), ud.grad, Kd.grad, sd.grad
+                return (o.detach(),) + torch.autograd.grad(o.square().mean(), (ud, Kd, sd))
             a, b, c_, d = single()
             ref_fin.copy_(a), ref_gu.copy_(b), ref_gk.copy_(c_), ref_gs.copy_(d)
             del a, b, c_, d
             single_ms[0] = time_fn(single, reps, warm=1)
-            del u_full
+            del u_full, ud
         for t in (ref_fin, ref_gu, ref_gk, ref_gs, single_ms):
             dist.broadcast(t, 0)
         sl = slice(slab.row0, slab.row0 + slab.Hs)

@@ -231,6 +231,12 @@ class SlabPeerBuffers:
         if self.hdl is not None:
             self.hdl.barrier()
 
+    def input_view(self) -> torch.Tensor:
+        """The owned rows of the initial-state buffer, [B,C,Hs,W] (strided): an initial condition written here
+        is used in place by `slab_rollout_fwd_bwd_p2p` (no slab-sized copy at the start of a pass)."""
+        h2 = 2 * self.slab.halo
+        return self.state[0][:, :, h2:h2 + self.slab.Hs]
+
     def _peer_view(self, peer: int, elem_off: int, shape):
         return self.hdl.get_buffer(peer, tuple(shape), self.flat.dtype, elem_off)
 
@@ -255,17 +261,22 @@ class SlabPeerBuffers:
 
 def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u_local: torch.Tensor,
                              kernels: torch.Tensor, symnet: torch.Tensor, L: int, dt: float, steps: int,
-                             grad_last_local: Callable, keep_features: Optional[bool] = None):
+                             grad_last_local: Callable, keep_features: Optional[bool] = None,
+                             copy_outputs: bool = True):
     """``SlabDecomposition.rollout_fwd_bwd`` with the halo exchanges fused into the step kernels
     (peer stores into the neighbours' ghost rows, `SlabPeerBuffers`).  The initial state and the loss
     seed fill the neighbours' ghost rows with peer copies (`SlabPeerBuffers.fill_ghosts`): no NCCL
     point-to-point on the path.  ``grad_last_local`` may accept ``out=`` (a strided view of the adjoint
-    buffer) to write the seed in place."""
+    buffer) to write the seed in place.  ``u_local`` may be ``bufs.input_view()`` itself (used in place).
+    ``copy_outputs=False`` returns the final state and the input gradient as strided VIEWS of the
+    persistent buffers (valid until the next pass) instead of contiguous copies."""
     from . import ops
     h, h2, Hs = slab.halo, 2 * slab.halo, slab.Hs
     B, C, _, W = u_local.shape
     feats = _slab_feature_buffers(keep_features, steps, B, C, kernels.shape[0], Hs, W, u_local)
-    bufs.state[0][:, :, h2:h2 + Hs] = u_local
+    own = bufs.input_view()
+    if not (u_local.data_ptr() == own.data_ptr() and u_local.stride() == own.stride()):
+        own.copy_(u_local)
     bufs.barrier()                                   # every rank is done with the buffers of its previous pass
     bufs.fill_ghosts("state", 0, h2)
     bufs.barrier()                                   # the neighbours' rows have landed
@@ -274,7 +285,9 @@ def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u
         ops.slab_step(bufs.state[t], kernels, symnet, L, dt, h2, bufs.state[t + 1], h2, up, dn, h2,
                       feats=None if feats is None else feats[t])
         bufs.barrier()                               # neighbours' boundary rows have landed
-    final = bufs.state[steps][:, :, h2:h2 + Hs].contiguous()
+    final = bufs.state[steps][:, :, h2:h2 + Hs]
+    if copy_outputs:
+        final = final.contiguous()
     cur = 0
     seed_view = bufs.lam[cur][:, :, h:h + Hs]
     try:
@@ -294,7 +307,8 @@ def slab_rollout_fwd_bwd_p2p(slab: "SlabDecomposition", bufs: SlabPeerBuffers, u
         cur ^= 1
     gk, gs = bwd.finish()
     flat_allreduce([gk, gs], group=slab.group)
-    return final, bufs.lam[cur][:, :, h:h + Hs].contiguous(), gk, gs
+    grad_u0 = bufs.lam[cur][:, :, h:h + Hs]
+    return final, (grad_u0.contiguous() if copy_outputs else grad_u0), gk, gs
 
 
 def chunked_fwd_bwd(model, u0: torch.Tensor, T: float, loss_scale: float, chunk: int) -> torch.Tensor:

@@ -62,6 +62,17 @@ def main():
 
     fin, gu, gk, gs = run()
     torch.cuda.synchronize()
+    if a.p2p:
+        # the in-place variant (input already in the symmetric buffer, outputs as views, seed written in place) must
+        # give the same bits
+        def seed_out(f, out=None):
+            return torch.mul(f, 2.0 / n_total, out=out)
+        pb.input_view().copy_(mine)
+        f2, g2, k2, s2 = PP.slab_rollout_fwd_bwd_p2p(slab, pb, pb.input_view(), Ks, sym, L, dt, a.steps, seed_out,
+                                                     keep_features=a.keep == "on", copy_outputs=False)
+        same = all(torch.equal(x, y) for x, y in ((fin, f2), (gu, g2), (gk, k2), (gs, s2)))
+        assert same, "in-place slab pass differs from the copying one"
+        del f2, g2
     errs = None
     if not a.no_check:
         ud, Kd, sd = [t.clone().requires_grad_(True) for t in (u_full, Ks, sym)]
