@@ -578,7 +578,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
     if (rc) return rc;
     const int n = N * kk;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, slots, N, kk, vlb, grad_kernels);
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, slots, N, kk, vlb, n, grad_kernels);
   }
   return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
 }
@@ -741,7 +741,7 @@ static int slab_bwd_end(void *workspace, size_t ws_bytes, T *grad_kernels, T *gr
     const int n = N * k * k;
     ProfScope ps(4, st);
     reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>((double *)(ws + lay.off_dk), lay.dk_slots, N, k * k, lay.vlb,
-                                                         grad_kernels);
+                                                         n, grad_kernels);
   }
   if (grad_symnet) {
     const int n = C * symnet_param_count(C * N, L);
@@ -896,7 +896,7 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
     const int n = N * k * k;
     ProfScope ps(4, st);
     T *bank = upwind ? (T *)(ws + lay.off_bank) : grad_kernels;
-    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, bank);
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, n, bank);
     if (upwind) // dK of a twin is the mirrored, negated contribution to its central filter
       upwind_fold_kernel<T><<<(Ns * k * k + 127) / 128, 128, 0, st>>>(bank, Ns, k, grad_kernels);
   }
@@ -1174,13 +1174,13 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   const int kk = k * k;
   if (grad_id_kernel) {
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<reduce_blocks(kk), 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, grad_id_kernel);
+    reduce_dk_kernel<T><<<reduce_blocks(kk), 128, 0, st>>>(dkp, lay.dk_slots, N + 1, kk, lay.vlb, kk, grad_id_kernel);
   }
   if (grad_kernels) {
     // filters 1..N: same partial layout, shifted by one filter
     const int n = N * kk;
     ProfScope ps(4, st);
-    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb,
+    reduce_dk_kernel<T><<<reduce_blocks(n), 128, 0, st>>>(dkp + lay.vlb, lay.dk_slots, N + 1, kk, lay.vlb, n,
                                                          grad_kernels);
   }
   if (grad_coe) {

@@ -16,9 +16,11 @@ __device__ __forceinline__ double warp_sum_fixed(double s) {
 
 // out[n*KK + e] = sum over slots of partial[slot][n][e]
 template <typename T>
-__global__ void reduce_dk_kernel(const double *partial, int n_slots, int N, int KK, int VLB, T *out) {
+__global__ void reduce_dk_kernel(const double *partial, int n_slots, int N, int KK, int VLB, int n_out, T *out) {
+  // N = filters per slot in the partial layout; n_out <= N*KK = elements of `out` (the launch is rounded up to whole
+  // blocks, and a caller may reduce only the first filters of the layout: never write past n_out)
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= N * KK) return;
+  if (i >= n_out) return;
   const int n = i / KK, e = i % KK;
   double s = 0.0;
   for (int sl = lane; sl < n_slots; sl += 32) s += partial[((size_t)sl * N + n) * VLB + e];

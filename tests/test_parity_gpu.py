@@ -1321,3 +1321,180 @@ def test_property_cuda_rollout_matches_oracle(P, cuda_device, k, bank, L, B, H, 
     assert rel(ud.grad, uc.grad) < tol
     assert rel(Kd.grad, Kc.grad) < tol
     assert rel(sd.grad, sc.grad) < tol
+
+
+# ---- memory safety without compute-sanitizer (closed on this pool): every buffer of a C-ABI call is carved out of
+# one arena pre-filled with a sentinel byte, with guard zones between the buffers; after the calls the guard zones
+# must be untouched.  Odd sizes (widths that are not a multiple of the vector width, partial tiles, single tiles).
+class _Arena:
+    GUARD, FILL = 8192, 0xA5
+
+    def __init__(self, nbytes, dev):
+        self.buf = torch.full((nbytes,), self.FILL, dtype=torch.uint8, device=dev)
+        self.off, self.regions = self.GUARD, []
+
+    def take(self, shape, dtype, name=""):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        start = (self.off + 255) // 256 * 256
+        assert start + n + self.GUARD <= self.buf.numel(), "arena too small"
+        self.regions.append((start, start + n, name or "buffer %d" % len(self.regions)))
+        self.off = start + n + self.GUARD
+        return self.buf[start:start + n].view(dtype).view(shape)
+
+    def guards_intact(self):
+        """True, or a description of the first damaged guard byte (which buffer it follows, how far past its end)."""
+        mask = torch.ones(self.buf.numel(), dtype=torch.bool, device=self.buf.device)
+        for a, b, _ in self.regions:
+            mask[a:b] = False
+        bad = torch.nonzero(mask & (self.buf != self.FILL))
+        if bad.numel() == 0:
+            return True
+        first, last = int(bad[0]), int(bad[-1])
+        prev = max((r for r in self.regions if r[1] <= first), key=lambda r: r[1], default=(0, 0, "arena start"))
+        nxt = min((r for r in self.regions if r[0] > first), key=lambda r: r[0], default=(self.buf.numel(),) * 2 + ("end",))
+        return "%d damaged guard bytes, first %d bytes past the end of '%s' (%d before '%s'), last at +%d" % (
+            bad.numel(), first - prev[1], prev[2], nxt[0] - first, nxt[2], last - prev[1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("keep", [False, True], ids=["recompute", "kept"])
+@pytest.mark.parametrize("shape", [(1, 2, 37, 53), (2, 2, 64, 100), (1, 1, 130, 66), (3, 2, 9, 12), (2, 2, 128, 128)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_no_writes_outside_outputs(P, cuda_device, tile_policy, dtype, keep, shape):
+    from pdenet_b200 import _lib
+    from pdenet_b200.ops import _ptr, _stream
+    B, C, H, W = shape
+    k, L, steps = 7, 2, 3
+    dx = 2 * math.pi / W
+    orders, M, scales, sym = make_model(k, 2, C, L, dx, seed=5)
+    N = len(orders)
+    Ks = P.m2k(M.to(cuda_device), scales).to(dtype)
+    es = torch.empty((), dtype=dtype).element_size()
+    ws_bytes = _lib.lib().pdenet_rollout_bwd_workspace_bytes(es, B, C, H, W, k, N, L, 0)
+    n_state = B * C * H * W
+    total = (2 + 2 * steps + (steps * N if keep else 0)) * n_state * es + ws_bytes + (1 << 20)
+    A = _Arena(total, cuda_device)
+    u0 = A.take((B, C, H, W), dtype, "u0")
+    kern = A.take((N, k, k), dtype, "kernels")
+    symn = A.take(tuple(sym.shape), dtype, "symnet")
+    states = A.take((steps, B, C, H, W), dtype, "states")
+    feats = A.take((steps, B, C * N, H, W), dtype, "feats") if keep else None
+    grad = A.take((steps, B, C, H, W), dtype, "grad_states")
+    gu, gk = A.take((B, C, H, W), dtype, "grad_u0"), A.take((N, k, k), dtype, "grad_kernels")
+    gs = A.take(tuple(sym.shape), dtype, "grad_symnet")
+    ws = A.take((ws_bytes,), torch.uint8, "workspace")
+    u0.copy_(smooth_field(B, C, H, W, 3).to(cuda_device, dtype))
+    kern.copy_(Ks)
+    symn.copy_(sym.to(cuda_device, dtype))
+    grad.copy_(torch.randn(steps, B, C, H, W, dtype=torch.float64, generator=torch.Generator().manual_seed(1)))
+    dt = 1e-3 * dx * dx
+    if keep:
+        _lib.check(_lib.fn("pdenet_rollout_fwd_keep", dtype)(_ptr(u0), _ptr(kern), _ptr(symn), _ptr(states), _ptr(feats),
+                                                            B, C, H, W, k, N, L, steps, dt, _stream()), "fwd_keep")
+        _lib.check(_lib.fn("pdenet_rollout_bwd_kept", dtype)(
+            _ptr(u0), _ptr(states), _ptr(feats), _ptr(grad), _lib.GRAD_ALL, _ptr(kern), _ptr(symn), _ptr(gu), _ptr(gk),
+            _ptr(gs), _ptr(ws), ws_bytes, 0, B, C, H, W, k, N, L, steps, dt, _stream()), "bwd_kept")
+    else:
+        _lib.check(_lib.fn("pdenet_rollout_fwd", dtype)(_ptr(u0), _ptr(kern), _ptr(symn), _ptr(states), B, C, H, W, k, N,
+                                                       L, steps, dt, _stream()), "fwd")
+        _lib.check(_lib.fn("pdenet_rollout_bwd", dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_ALL, _ptr(kern), _ptr(symn), _ptr(gu), _ptr(gk), _ptr(gs),
+            _ptr(ws), ws_bytes, 0, B, C, H, W, k, N, L, steps, dt, _stream()), "bwd")
+    torch.cuda.synchronize()
+    assert A.guards_intact() is True, A.guards_intact()
+    for t in (states, gu, gk, gs):
+        assert torch.isfinite(t).all()
+    # and the arena run agrees with the ordinary op
+    ud, Kd, sd = [t.detach().clone().requires_grad_(True) for t in (u0, kern, symn)]
+    out = P.rollout(ud, Kd, sd, L, dt, steps, keep_features=keep)
+    out.backward(grad)
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    assert rel(states, out) <= tol and rel(gu, ud.grad) <= tol and rel(gk, Kd.grad) <= tol and rel(gs, sd.grad) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("small_path", [True, False], ids=["cluster", "tiled"])
+@pytest.mark.parametrize("shape", [(3, 50, 50, 5, 4), (2, 37, 53, 5, 2), (1, 64, 100, 7, 2), (5, 20, 24, 3, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_no_writes_outside_outputs_linear(P, cuda_device, dtype, small_path, shape):
+    """Guard zones around every buffer of the PDE-Net 1 linear rollout (cluster-resident and tiled paths)."""
+    from pdenet_b200 import _lib
+    from pdenet_b200.modules import order_list
+    from pdenet_b200.ops import _ptr, _stream
+    B, H, W, k, max_order = shape
+    steps = 4
+    dx = 2 * math.pi / W
+    g = torch.Generator().manual_seed(11)
+    orders = [o for o in order_list(max_order) if o != (0, 0) and o[0] < k and o[1] < k]
+    N = len(orders)
+    M = torch.zeros(N + 1, k, k, dtype=torch.float64)
+    M[0, 0, 0] = 1
+    for n, (a, b) in enumerate(orders):
+        M[n + 1, a, b] = 1
+    M = M + 1e-3 * torch.randn(M.shape, generator=g, dtype=torch.float64)
+    ks = P.m2k(M.to(cuda_device), [1.0] + [1.0 / dx ** (a + b) for a, b in orders]).to(dtype)
+    es = torch.empty((), dtype=dtype).element_size()
+    prev = _lib.lib().pdenet_linear_small_grid_path(1 if small_path else 0)
+    try:
+        ws_bytes = _lib.lib().pdenet_linear_rollout_bwd_workspace_bytes(es, B, H, W, k, N)
+        A = _Arena((2 + 2 * steps) * B * H * W * es + 2 * N * H * W * es + ws_bytes + (1 << 20), cuda_device)
+        u0, k0 = A.take((B, H, W), dtype, "u0"), A.take((k, k), dtype, "id_kernel")
+        kern, coe = A.take((N, k, k), dtype, "kernels"), A.take((N, H, W), dtype, "coe")
+        states, grad = A.take((steps, B, H, W), dtype, "states"), A.take((steps, B, H, W), dtype, "grad_states")
+        gu, gk0 = A.take((B, H, W), dtype, "grad_u0"), A.take((k, k), dtype, "grad_id_kernel")
+        gk, gc = A.take((N, k, k), dtype, "grad_kernels"), A.take((N, H, W), dtype, "grad_coe")
+        ws = A.take((ws_bytes,), torch.uint8, "workspace")
+        u0.copy_(smooth_field(B, 1, H, W, 3)[:, 0].to(cuda_device, dtype))
+        k0.copy_(ks[0])
+        kern.copy_(ks[1:])
+        coe.copy_(torch.randn(N, H, W, generator=g, dtype=torch.float64))
+        grad.copy_(torch.randn(steps, B, H, W, generator=g, dtype=torch.float64))
+        dt = 1e-3 * dx ** max_order
+        _lib.check(_lib.fn("pdenet_linear_rollout_fwd", dtype)(_ptr(u0), _ptr(k0), _ptr(kern), _ptr(coe), _ptr(states), B, H,
+                                                              W, k, N, steps, dt, _stream()), "linear fwd")
+        _lib.check(_lib.fn("pdenet_linear_rollout_bwd", dtype)(
+            _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_ALL, _ptr(k0), _ptr(kern), _ptr(coe), _ptr(gu), _ptr(gk0),
+            _ptr(gk), _ptr(gc), _ptr(ws), ws_bytes, B, H, W, k, N, steps, dt, _stream()), "linear bwd")
+        torch.cuda.synchronize()
+        assert A.guards_intact() is True, A.guards_intact()
+        for t in (states, gu, gk0, gk, gc):
+            assert torch.isfinite(t).all()
+    finally:
+        _lib.lib().pdenet_linear_small_grid_path(prev)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape", [(1, 2, 37, 53), (2, 1, 64, 100), (2, 2, 128, 128)], ids=lambda s: "x".join(map(str, s)))
+def test_no_writes_outside_outputs_upwind(P, cuda_device, dtype, shape):
+    """Guard zones around every buffer of the pseudo-upwind rollout (forward and reverse)."""
+    from pdenet_b200 import _lib
+    from pdenet_b200.ops import _ptr, _stream
+    B, C, H, W = shape
+    k, L, steps = 5, 2, 3
+    dx = 2 * math.pi / W
+    orders, M, scales, sym = make_model(k, 2, C, L, dx, seed=5)
+    N = len(orders)
+    Ks = P.m2k(M.to(cuda_device), scales).to(dtype)
+    es = torch.empty((), dtype=dtype).element_size()
+    ws_bytes = _lib.lib().pdenet_rollout_bwd_upwind_workspace_bytes(es, B, C, H, W, k, N, L, 0)
+    A = _Arena((2 + 2 * steps) * B * C * H * W * es + ws_bytes + (1 << 20), cuda_device)
+    u0, kern = A.take((B, C, H, W), dtype, "u0"), A.take((N, k, k), dtype, "kernels")
+    symn = A.take(tuple(sym.shape), dtype, "symnet")
+    states, grad = A.take((steps, B, C, H, W), dtype, "states"), A.take((steps, B, C, H, W), dtype, "grad_states")
+    gu, gk = A.take((B, C, H, W), dtype, "grad_u0"), A.take((N, k, k), dtype, "grad_kernels")
+    gs = A.take(tuple(sym.shape), dtype, "grad_symnet")
+    ws = A.take((ws_bytes,), torch.uint8, "workspace")
+    u0.copy_(smooth_field(B, C, H, W, 3).to(cuda_device, dtype))
+    kern.copy_(Ks)
+    symn.copy_(sym.to(cuda_device, dtype))
+    grad.copy_(torch.randn(steps, B, C, H, W, dtype=torch.float64, generator=torch.Generator().manual_seed(1)))
+    dt = 1e-3 * dx * dx
+    _lib.check(_lib.fn("pdenet_rollout_fwd_upwind", dtype)(_ptr(u0), _ptr(kern), _ptr(symn), _ptr(states), B, C, H, W, k,
+                                                          N, L, steps, dt, _stream()), "fwd_upwind")
+    _lib.check(_lib.fn("pdenet_rollout_bwd_upwind", dtype)(
+        _ptr(u0), _ptr(states), _ptr(grad), _lib.GRAD_ALL, _ptr(kern), _ptr(symn), _ptr(gu), _ptr(gk), _ptr(gs),
+        _ptr(ws), ws_bytes, 0, B, C, H, W, k, N, L, steps, dt, _stream()), "bwd_upwind")
+    torch.cuda.synchronize()
+    assert A.guards_intact() is True, A.guards_intact()
+    for t in (states, gu, gk, gs):
+        assert torch.isfinite(t).all()
