@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(FGradCfg<T, K, MT_>::NT, kFGradCtasPerSm) filt
   T kacc[VLB];
 #pragma unroll
   for (int e = 0; e < VLB; ++e) kacc[e] = T(0);
-  double *slot = p.dk_partial + ((size_t)(blockIdx.x * (NTHREADS / 32) + part) * N + n) * VLB;
+  double *slot = p.dk_partial + ((size_t)(blockIdx.x * p.slot_stride + part) * N + n) * VLB;
   // fp32: the per-lane accumulators are widened once per ITEM (<= MT*RW*VEC products each in single
   // precision), the cross-lane sum and everything after it run in double -- the error of the filter
   // gradient then no longer grows with the grid size or the batch.  fp64 reduces once per launch.

@@ -438,7 +438,25 @@ static int run_adjoint(AdjParams<T> &p, int B, int C, int N, int H, int W, cudaS
 // Filter gradient: warps own filters; N filters are covered by launches of nw in {6, 3, 2, 1}
 // filters each (nw divides the warps of a CTA; the other warps split the tile rows).  Geometry
 // (kFGradWarps, kFGradCtasPerSm): params.cuh.
-static int dk_slot_count(int sms) { return sms * kFGradCtasPerSm * kFGradWarps; }
+static int fgrad_nw(int left) { // largest divisor of the CTA's warp count that does not exceed the filters left
+  int nw = 1;
+  for (int d = 1; d <= kFGradWarps; ++d)
+    if (kFGradWarps % d == 0 && d <= left) nw = d;
+  return nw;
+}
+// row parts per CTA of the launch that splits the rows most finely (= partial slots a CTA needs): the partial
+// buffer and its final reduction cover sms * CTAs * this many slots, not one per warp (N = 6: 2 instead of 12 --
+// the reduction of a small problem was its longest kernel)
+static int fgrad_max_parts(int N) {
+  int mp = 1;
+  for (int n0 = 0; n0 < N;) {
+    const int nw = fgrad_nw(N - n0);
+    if (kFGradWarps / nw > mp) mp = kFGradWarps / nw;
+    n0 += nw;
+  }
+  return mp;
+}
+static int dk_slot_count(int sms, int N) { return sms * kFGradCtasPerSm * fgrad_max_parts(N); }
 
 template <typename T, int K>
 static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W, cudaStream_t st) {
@@ -461,12 +479,10 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
   p.vec_ok = (W % vec == 0) && (((uintptr_t)p.g) % 16 == 0) ? 1 : 0;
   const int cap = sms * kFGradCtasPerSm;
   const int grid = p.n_items < cap ? p.n_items : cap;
+  p.slot_stride = fgrad_max_parts(N);
   int n0 = 0;
   while (n0 < N) {
-    const int left = N - n0;
-    int nw = 1; // largest divisor of the CTA's warp count that does not exceed the filters left
-    for (int d = 1; d <= kFGradWarps; ++d)
-      if (kFGradWarps % d == 0 && d <= left) nw = d;
+    const int nw = fgrad_nw(N - n0);
     p.n0 = n0;
     p.nw = nw;
     ProfScope ps(3, st);
@@ -544,7 +560,7 @@ static int fd2d_bwd(const T *u, const T *grad_feats, const T *kernels, T *grad_u
     return PDENET_E_BADARG;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64), slots = dk_slot_count(sms);
+  const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64), slots = dk_slot_count(sms, N);
   const size_t need = (size_t)slots * N * vlb * sizeof(double);
   if (ws_bytes < need) return PDENET_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -628,7 +644,7 @@ static SlabLayout slab_layout(size_t es, int B, int C, int Hs, int W, int k, int
   SlabLayout l;
   const int kk = k * k, r = (k - 1) / 2;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  l.dk_slots = dk_slot_count(sms);
+  l.dk_slots = dk_slot_count(sms, N);
   l.sym_slots = sms * kSymSlotsPerSm;
   size_t o = 0;
   l.off_g = o;
@@ -762,7 +778,7 @@ static BwdLayout bwd_layout(size_t es, int B, int C, int H, int W, int k, int N,
   l.chunk = (batch_chunk <= 0 || batch_chunk > B) ? B : batch_chunk;
   const int kk = k * k;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  l.dk_slots = dk_slot_count(sms);
+  l.dk_slots = dk_slot_count(sms, N);
   l.sym_slots = sms * kSymSlotsPerSm;
   const size_t img = (size_t)H * W;
   size_t o = 0;
@@ -1031,7 +1047,7 @@ static LinLayout lin_layout(size_t es, int B, int H, int W, int k, int N, int sm
   LinLayout l;
   const int kk = k * k;
   l.vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  l.dk_slots = dk_slot_count(sms);
+  l.dk_slots = dk_slot_count(sms, N + 1);
   const size_t img = (size_t)H * W;
   size_t o = 0;
   l.off_g = o;
@@ -1590,7 +1606,7 @@ size_t pdenet_fd2d_bwd_workspace_bytes(int k, int N) {
   const int sms = sm_count();
   if (sms <= 0 || k <= 0 || N <= 0) return 0;
   const int kk = k * k, vlb = kk <= 16 ? 16 : (kk <= 32 ? 32 : 64);
-  return (size_t)dk_slot_count(sms) * N * vlb * sizeof(double);
+  return (size_t)dk_slot_count(sms, N) * N * vlb * sizeof(double);
 }
 int pdenet_fd2d_bwd_f64(const double *u, const double *grad_feats, const double *kernels, double *grad_u,
                         double *grad_kernels, void *workspace, size_t workspace_bytes, int B, int C, int H, int W,

@@ -134,7 +134,8 @@ template <typename T> struct FGradParams {
   const T *u; // [B][C][u_rows][W]
   int u_rows, u_off;
   int wrap_y;
-  double *dk_partial; // [gridDim.x * 6][N][VLB], accumulated across launches
+  double *dk_partial; // [gridDim.x * slot_stride][N][VLB], accumulated across launches
+  int slot_stride;    // partial slots per CTA = the largest `parts` of any launch of this bank (host: fgrad_max_parts)
   int n0, nw;         // this launch handles filters n0 .. n0+nw-1; warp w -> filter n0 + w % nw,
                       // row part w / nw of `parts` = NWARPS / nw (nw divides NWARPS)
   int vec_ok;         // 1 if g rows may be read with 16-byte loads (W % VEC == 0, base aligned)
