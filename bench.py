@@ -381,10 +381,20 @@ def small_configs_record(P, dev, peaks_tflops):
 
         ms, msg = time_fn(fn, 20), time_graph(fn)
         pts = B * H * W * steps
+        # the library's own training closure (losses.GraphedTrainingLoss: POLYPDE2D rollout, fused MSE against
+        # observed states of every block, reverse pass, flat gradient -- captured once INSIDE the library, the
+        # caller only replays): no user-side graph
+        from pdenet_b200 import losses
+        model, _ = build_model(P, dev, dtype, H, W, 0, True)
+        observed = torch.stack([u0] * steps)
+        closure = losses.GraphedTrainingLoss(model, u0, observed)
+        msc = time_fn(closure, 50)
         out.append({"config": name, "dtype": tag, "ms_fwd_bwd": ms, "ms_fwd_bwd_cuda_graph": msg,
+                    "ms_library_graphed_training_closure": msc,
                     "grid_point_steps_per_s": pts / (ms * 1e-3), "grid_point_steps_per_s_cuda_graph": pts / (msg * 1e-3),
                     "frac_of_fma_peak": F_TOTAL * pts / (ms * 1e-3) / (peaks_tflops[tag] * 1e12),
                     "frac_of_fma_peak_cuda_graph": F_TOTAL * pts / (msg * 1e-3) / (peaks_tflops[tag] * 1e12)})
+        del closure, model
 
     def linear_cfg(name, B, H, W, steps, k=5, max_order=4):
         dx = 2 * math.pi / W
