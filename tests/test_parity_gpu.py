@@ -888,6 +888,22 @@ def test_streamed_fwd_bwd_equals_resident(P, cuda_device):
     assert abs(loss.item() - ref_loss.item()) < 1e-12 * abs(ref_loss.item())
     for p, r in zip(model.parameters(), ref):
         assert rel(p.grad, r) < 1e-11
+    # passes pipelined over the pass boundary (the first chunk of pass p+1 is copied behind the last chunk of pass
+    # p): every pass gives the same loss and gradients; chunk counts 3 (odd: the buffer parity flips every pass),
+    # 4, and 1 (the prefetch targets the buffer that was just used); the host batch changes between passes of
+    # the last run only AFTER the pass that prefetched it was issued, so the prefetched chunk is the old one --
+    # documented behaviour: a new batch needs a new StreamedBatch
+    for chunk, ramp in ((3, False), (2, True), (7, False)):
+        sb = PP.StreamedBatch(host, chunk, cuda_device, ramp=ramp, prefetch_next=True)
+        for _ in range(4):
+            for p in model.parameters():
+                p.grad = None
+            loss = sb.run(model, 3 * dt, scale)
+            torch.cuda.synchronize()
+            assert abs(loss.item() - ref_loss.item()) < 1e-12 * abs(ref_loss.item()), (chunk, ramp)
+            for p, r in zip(model.parameters(), ref):
+                assert rel(p.grad, r) < 1e-11
+        assert sb.issued == sb.g + 1          # exactly one chunk in flight for the next pass
     # the resident chunked pass of bench.py (ragged last chunk), features kept and recomputed
     for keep in (True, False):
         for p in model.parameters():
