@@ -833,8 +833,9 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
   double *dkp = (double *)(ws + lay.off_dk);
   double *symp = (double *)(ws + lay.off_sym);
   const int Psym = symnet_param_count(C * Ns, L);
-  if (cudaMemsetAsync(dkp, 0, (size_t)lay.dk_slots * N * lay.vlb * sizeof(double), st) != cudaSuccess ||
-      cudaMemsetAsync(symp, 0, (size_t)lay.sym_slots * C * Psym * sizeof(double), st) != cudaSuccess)
+  // the two partial regions are adjacent in the workspace (bwd_layout): one memset node for both
+  if (cudaMemsetAsync(dkp, 0, (lay.off_sym - lay.off_dk) + (size_t)lay.sym_slots * C * Psym * sizeof(double), st) !=
+      cudaSuccess)
     return PDENET_E_CUDA;
 
   SlotLease lease(st);
@@ -907,6 +908,13 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
     lam_in = lam_out;
     cur ^= 1;
     if (!lam_out && t > 0) return PDENET_E_BADARG; // unreachable: lam_out is only NULL at t == 0
+  }
+  if (grad_kernels && grad_symnet && !upwind) { // the usual case: both finishing reductions in one launch
+    const int n = N * k * k, ns = C * Psym;
+    ProfScope ps(4, st);
+    reduce_grads_kernel<T><<<reduce_blocks(n + ns), 128, 0, st>>>(dkp, lay.dk_slots, N, k * k, lay.vlb, n, grad_kernels,
+                                                                  symp, lay.sym_slots, ns, grad_symnet);
+    return cudaGetLastError() == cudaSuccess ? PDENET_OK : PDENET_E_CUDA;
   }
   if (grad_kernels) {
     const int n = N * k * k;

@@ -36,6 +36,28 @@ template <typename T> __global__ void reduce_flat_kernel(const double *partial, 
   s = warp_sum_fixed(s);
   if (lane == 0) out[i] = (T)s;
 }
+// both finishing reductions of a reverse rollout in ONE launch (a small pass is a chain of dependent launches of a
+// few microseconds each): warps [0, n_dk) do what reduce_dk_kernel does, warps [n_dk, n_dk + n_sym) what
+// reduce_flat_kernel does -- same addends in the same order, bit-identical to the two separate launches
+template <typename T>
+__global__ void reduce_grads_kernel(const double *dk_partial, int dk_slots, int N, int KK, int VLB, int n_dk, T *dk_out,
+                                    const double *sym_partial, int sym_slots, int n_sym, T *sym_out) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  if (i < n_dk) {
+    const int n = i / KK, e = i % KK;
+    for (int sl = lane; sl < dk_slots; sl += 32) s += dk_partial[((size_t)sl * N + n) * VLB + e];
+    s = warp_sum_fixed(s);
+    if (lane == 0) dk_out[i] = (T)s;
+    return;
+  }
+  i -= n_dk;
+  if (i >= n_sym) return;
+  for (int sl = lane; sl < sym_slots; sl += 32) s += sym_partial[(size_t)sl * n_sym + i];
+  s = warp_sum_fixed(s);
+  if (lane == 0) sym_out[i] = (T)s;
+}
 // ---- fused MSE loss + gradient seed (row f-3) ----------------------------------------------------
 constexpr int kMseBlocks = 512; // partial sums per launch (fixed => reproducible)
 struct MseWeights {

@@ -96,14 +96,36 @@ class GraphedTrainingLoss:
         self.flat = model.__dict__.get("_flat") or FlatParams(model)
         self.params = self.flat.params
         self.u0, self.observed = u0.detach().clone(), observed.detach().clone()
-        kw = dict(block_weights=block_weights, sparsity=sparsity, momentsparsity=momentsparsity,
-                  symnet_threshold=symnet_threshold, moment_threshold=moment_threshold)
+
+        # The model's own grad_proj (zero the gradient of pinned moment entries) is a no-op here: the gradient
+        # buffer starts from zero and both sources of moment gradients -- the reverse of the moment -> kernel map
+        # (pinned mask applied inside pdenet_m2k_bwd_*) and the moment sparsity term (masked) -- leave pinned
+        # entries at exactly zero.  Skipping it takes one launch per filter out of the captured chain; a
+        # user-supplied projection is still applied.
+        own_proj = getattr(model, "diff_grad_proj", None)
+        self._skip_grad_proj = bool(getattr(model, "pinned_gradients_masked", False)) and \
+            own_proj is not None and self.flat.grad_proj == own_proj
+        blocks = self.observed.shape[0]
 
         def evaluate():
+            # same arithmetic as training_loss(...).backward(), bit for bit, with the reverse rollout seeded
+            # directly by the fused MSE pass: no ones-filled root gradient, no `seed * 1` pass over the states
             self.flat.zero_grad()
-            loss = training_loss(model, self.u0, self.observed, **kw)
-            loss.backward()
-            return loss.detach(), self.flat.grad_flat()
+            states = model.multistep(self.u0, blocks, all_states=True)
+            loss, seed = ops.mse_seed(states, self.observed, block_weights)
+            roots, seeds = [states], [seed]
+            if sparsity:
+                reg = (blocks * sparsity) * symnet_sparsity(model, symnet_threshold)
+                loss = loss + reg.detach()
+                roots.append(reg)
+                seeds.append(None)
+            if momentsparsity:
+                reg = (blocks * momentsparsity) * moment_sparsity(model, moment_threshold)
+                loss = loss + reg.detach()
+                roots.append(reg)
+                seeds.append(None)
+            torch.autograd.backward(roots, seeds)
+            return loss, (self.flat.gflat if self._skip_grad_proj else self.flat.grad_flat())
 
         cur = torch.cuda.current_stream(u0.device)
         side = torch.cuda.Stream(u0.device)

@@ -165,6 +165,10 @@ class POLYPDE2D(nn.Module):
     ``scheme``: ``'central'`` or ``'upwind'`` (pseudo-upwind first-order inputs, row f-1; supported for
     ``max_order`` 1-2 and up to two channels)."""
 
+    #: the moment gradients this model produces are already zero on pinned entries (the mask is applied inside
+    #: ``pdenet_m2k_bwd_*``, see ``_bank_kernels``): ``losses.GraphedTrainingLoss`` then skips ``diff_grad_proj``
+    pinned_gradients_masked = True
+
     def __init__(self, dt, dx, kernel_size, max_order, constraint, channel_names, hidden_layers=2,
                  scheme="central", dtype=torch.float64, batch_chunk=0, keep_features=None):
         super().__init__()

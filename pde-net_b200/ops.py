@@ -571,24 +571,34 @@ def single_nonlinear_rollout(u0, id_kernel, kernels, coe, fcoef, dt: float, step
                                          int(mesh), int(degree))
 
 
+def mse_seed(states: torch.Tensor, observed: torch.Tensor, weights: Optional[Sequence[float]] = None):
+    """``(loss, seed)`` without an autograd node: ``loss = sum_t w_t * mean((states[t]-observed[t])**2)`` (a 0-d
+    tensor of the states' dtype) and ``seed = d loss / d states`` from ONE pass over the states
+    (``pdenet_mse_seed_*``).  A caller that drives the reverse rollout itself (``states.backward(seed)``,
+    :class:`losses.GraphedTrainingLoss`) needs neither the ones-filled root gradient nor the ``seed * 1`` pass that
+    going through :func:`mse_loss` and ``loss.backward()`` costs."""
+    states = _req(states.detach(), "states")
+    observed = _req(observed.detach(), "observed", states.dtype)
+    if states.shape != observed.shape:
+        raise ValueError("states and observed must have the same shape [steps, ...]")
+    steps = states.shape[0]
+    n = states[0].numel()
+    grad = torch.empty_like(states)
+    loss = torch.empty((), dtype=torch.float64, device=states.device)
+    ws = torch.empty(64 * 512, dtype=torch.float64, device=states.device)
+    wh = None if weights is None else (C.c_double * steps)(*[float(w) for w in weights])
+    _lib.check(_lib.fn("pdenet_mse_seed", states.dtype)(_ptr(states), _ptr(observed), wh, _ptr(grad), _ptr(loss), n,
+                                                        steps, _ptr(ws), ws.numel() * 8, _stream()),
+               "pdenet_mse_seed")
+    return loss.to(states.dtype), grad
+
+
 class _MseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, states, observed, weights):
-        states = _req(states, "states")
-        observed = _req(observed.detach(), "observed", states.dtype)
-        if states.shape != observed.shape:
-            raise ValueError("states and observed must have the same shape [steps, ...]")
-        steps = states.shape[0]
-        n = states[0].numel()
-        grad = torch.empty_like(states)
-        loss = torch.empty((), dtype=torch.float64, device=states.device)
-        ws = torch.empty(64 * 512, dtype=torch.float64, device=states.device)
-        wh = None if weights is None else (C.c_double * steps)(*[float(w) for w in weights])
-        _lib.check(_lib.fn("pdenet_mse_seed", states.dtype)(_ptr(states), _ptr(observed), wh, _ptr(grad), _ptr(loss), n,
-                                                            steps, _ptr(ws), ws.numel() * 8, _stream()),
-                   "pdenet_mse_seed")
+        loss, grad = mse_seed(states, observed, weights)
         ctx.save_for_backward(grad)
-        return loss.to(states.dtype)
+        return loss
 
     @staticmethod
     def backward(ctx, gout):

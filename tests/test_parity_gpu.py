@@ -1135,10 +1135,14 @@ def test_training_loss_closure_matches_oracle(P, cuda_device):
     assert rel(gs, sc.grad) < 1e-9
 
 
-def test_graphed_training_loss_replays_bit_identically(P, cuda_device):
+@pytest.mark.parametrize("regularised", [True, False])
+def test_graphed_training_loss_replays_bit_identically(P, cuda_device, regularised):
     """The whole objective (rollout, MSE seed, sparsity terms, reverse rollout, flat gradient) as
     one CUDA graph: equals the eager evaluation bit for bit, and follows in-place parameter updates
-    and a new data batch without re-capture."""
+    and a new data batch without re-capture.  (The captured chain seeds the reverse rollout straight
+    from the fused MSE pass and skips the model's own grad_proj -- pinned entries are already zero --
+    so this is also the check that those short cuts change nothing; without the sparsity terms it is
+    the chain the bench times for BASELINE config 1.)"""
     dev = cuda_device
     k, max_order, C, L, B, H, W, blocks, dx, dt = 5, 2, 2, 2, 4, 32, 32, 3, 0.2, 1e-2
     model = P.POLYPDE2D(dt, dx, k, max_order, "moment", "u,v", hidden_layers=L).to(dev)
@@ -1151,7 +1155,7 @@ def test_graphed_training_loss_replays_bit_identically(P, cuda_device):
             p.copy_((0.05 * torch.randn(p.shape, generator=g, dtype=torch.float64)).to(dev))
     u0 = smooth_field(B, C, H, W, 92).to(dev)
     obs = (0.9 * P.rollout(u0, model.scaled_kernels().detach(), model.symnet_flat().detach(), L, dt, blocks)).detach()
-    kw = dict(block_weights=[1.0, 2.0, 0.5], sparsity=1e-3, momentsparsity=1e-3)
+    kw = dict(block_weights=[1.0, 2.0, 0.5], sparsity=1e-3, momentsparsity=1e-3) if regularised else {}
     flat = P.FlatParams(model)
 
     def eager(u, o):
@@ -1161,9 +1165,12 @@ def test_graphed_training_loss_replays_bit_identically(P, cuda_device):
         return loss.detach().clone(), flat.grad_flat().clone()
 
     graphed = P.losses.GraphedTrainingLoss(model, u0, obs, **kw)
+    assert graphed._skip_grad_proj
     l0, g0 = eager(u0, obs)
     l1, g1 = graphed()
     assert torch.equal(l1, l0) and torch.equal(g1, g0)
+    pinned = torch.cat([fd._pinned.reshape(-1) for fd in model.fds])
+    assert pinned.any() and not g1[:pinned.numel()][pinned].any()   # moments lead the flat buffer
     # in-place parameter update (what the L-BFGS bridge does) -> same graph, new values
     flat.set_flat(flat.get_flat() * 0.97)
     l0, g0 = eager(u0, obs)
