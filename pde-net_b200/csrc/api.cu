@@ -950,7 +950,7 @@ static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, in
     if (H / cs < r || H / cs < 1) return false; // every band must own the halo rows its neighbours fetch
     const int hb_max = (H + cs - 1) / cs;
     if ((long long)hb_max * W > (long long)kLinClusterThreads * pts_max) return false;
-    const size_t elems = (size_t)(N + 1) * kk + (size_t)(hb_max + 2 * r) * kk * W + 3 * (size_t)(hb_max + 2 * r) * W;
+    const size_t elems = (size_t)(N + 1) * kk + (size_t)(hb_max + 2 * r) * kk * W + 4 * (size_t)(hb_max + 2 * r) * W;
     if (elems * es > (size_t)220 * 1024) return false;
     pl.cs = cs;
     pl.hb_max = hb_max;
@@ -1124,7 +1124,7 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
       if (grad_id_kernel || grad_kernels || grad_coe) {
         T *Rsum = (T *)ws + (size_t)B * kk * img;
         ProfScope ps(4, st);
-        lin_cluster_dcoe_kernel<T><<<(unsigned)((img + 127) / 128), 128, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
+        lin_cluster_dcoe_kernel<T><<<(unsigned)((img + kDcoePts - 1) / kDcoePts), kDcoeThreads, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
                                                                                   grad_coe);
         if (grad_id_kernel || grad_kernels)
           lin_cluster_dk_kernel<T><<<dim3(kk, N + 1), 256, 0, st>>>(Rsum, coe, 0, img, kk, (T)dt, grad_id_kernel,
@@ -1376,7 +1376,7 @@ static int snl_bwd(const T *u0, const T *states, const T *grad_states, int grad_
   if (grad_k0 || grad_kernels || grad_coe) {
     T *Rsum = q.R + (size_t)B * kk * img;
     ProfScope ps(4, st);
-    lin_cluster_dcoe_kernel<T><<<(unsigned)((img + 127) / 128), 128, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
+    lin_cluster_dcoe_kernel<T><<<(unsigned)((img + kDcoePts - 1) / kDcoePts), kDcoeThreads, 0, st>>>(q.R, B, kk, img, kernels, N, (T)dt, Rsum,
                                                                               grad_coe ? field : nullptr);
     if (grad_coe) lin_cluster_dcoe_const_kernel<T><<<N, 256, 0, st>>>(field, img, grad_coe);
     if (grad_k0 || grad_kernels)

@@ -72,10 +72,12 @@ __device__ __forceinline__ void lagrange_eval_rt(T x, const T *coef, T lo, T inv
 __device__ __forceinline__ int band_start(int c, int H, int cs) { return (int)(((long long)c * H) / cs); }
 
 // shared-memory layout (elements of T): taps [(N+1)][KK] | w [(hb_max+2r)][KK][W] | buf0, buf1 [(hb_max+2r)][W]
+// (state / adjoint, double-buffered) | reverse only: ubuf0, ubuf1 [(hb_max+2r)][W] (u_t, double-buffered: the copy of
+// u_{t-1} runs behind the arithmetic of step t)
 template <typename T, int K> struct LinClusterSmem {
   static constexpr int R = (K - 1) / 2, KK = K * K;
   static __host__ __device__ size_t elems(int N, int hb_max, int W) {
-    return (size_t)(N + 1) * KK + (size_t)(hb_max + 2 * R) * KK * W + 3 * (size_t)(hb_max + 2 * R) * W;
+    return (size_t)(N + 1) * KK + (size_t)(hb_max + 2 * R) * KK * W + 4 * (size_t)(hb_max + 2 * R) * W;
   }
 };
 
@@ -153,7 +155,16 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_fwd_kern
 #pragma unroll
     for (int bb = 0; bb < K; ++bb) xm[q][bb] = wrap_index(px[q] + bb - R, W);
   }
+  // Halo rows of the NEXT state are pushed: the thread that computes a point of the first / last R rows of the band
+  // also stores it into the ring neighbour's halo row of the buffer being written (DSMEM store), so ONE cluster
+  // barrier separates two steps (the first version pulled the halos after the barrier and needed a second, block-wide
+  // barrier behind the pull: two barriers + a remote-load round trip per step on a path that is all latency).
+  // Safe: the neighbour's `nxt` was its `cur` one step ago, and it finished reading that before the last barrier.
+  const int up = (rank + cs - 1) % cs, dn = (rank + 1) % cs;
+  const int hb_up = band_start(up + 1, H, cs) - band_start(up, H, cs);
   T *cur = buf0, *nxt = buf1;
+  T *nxt_up = cluster.map_shared_rank(buf1, up), *cur_up = cluster.map_shared_rank(buf0, up);
+  T *nxt_dn = cluster.map_shared_rank(buf1, dn), *cur_dn = cluster.map_shared_rank(buf0, dn);
   const size_t stride = (size_t)p.B * H * W;
   for (int t = 0; t < p.steps; ++t) {
     T *out = p.states + (size_t)t * stride + (size_t)b * H * W + (size_t)y0 * W;
@@ -174,16 +185,19 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_fwd_kern
         acc = fma_(p.dt, fv, acc);
       }
       nxt[(R + py[q]) * W + px[q]] = acc;
+      if (py[q] < R) nxt_up[(R + hb_up + py[q]) * W + px[q]] = acc;          // bottom halo of the band above
+      if (py[q] >= hb - R) nxt_dn[(py[q] - (hb - R)) * W + px[q]] = acc;     // top halo of the band below
       out[py[q] * W + px[q]] = acc;
     }
-    cluster.sync(); // every interior of `nxt` is written; nobody still reads `cur`'s neighbours' halos
-    fetch_halo<T, K>(cluster, nxt, hb, W, H, cs, rank);
-    __syncthreads();
+    // interiors and halos of every `nxt` are written (release / acquire over the cluster); nobody reads `cur` any more.
+    // Also the last step: no CTA may exit while a neighbour can still store into its shared memory.
+    cluster.sync();
     T *tmp = cur;
     cur = nxt;
     nxt = tmp;
+    tmp = cur_up, cur_up = nxt_up, nxt_up = tmp;
+    tmp = cur_dn, cur_dn = nxt_dn, nxt_dn = tmp;
   }
-  cluster.sync(); // keep shared memory alive until every neighbour has fetched its last halo
 }
 
 // ---- reverse: all steps of one trajectory inside one cluster ---------------------------------------------
@@ -199,17 +213,30 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_bwd_kern
   T *w = taps + (p.N + 1) * KK;
   T *lam0 = w + (size_t)(p.hb_max + 2 * R) * KK * W;
   T *lam1 = lam0 + (size_t)(p.hb_max + 2 * R) * W;
-  T *ubuf = lam1 + (size_t)(p.hb_max + 2 * R) * W;
+  T *ucur = lam1 + (size_t)(p.hb_max + 2 * R) * W;
+  T *unxt = ucur + (size_t)(p.hb_max + 2 * R) * W;
   const int tid = threadIdx.x;
+  const size_t img = (size_t)H * W, stride = (size_t)p.B * img;
+  // u_t (band + halo rows, wrapped) from global memory, asynchronously (cp.async: the copy of u_{t-1} is issued before
+  // the arithmetic of step t and awaited behind it -- the first version loaded u_t synchronously at the top of a step)
+  auto stage_u = [&](int t, T *dst) {
+    const T *ut = (t == 0 ? p.u0 : p.states + (size_t)(t - 1) * stride) + (size_t)b * img;
+    for (int idx = tid; idx < (hb + 2 * R) * W; idx += blockDim.x) {
+      const int row = idx / W, x = idx - row * W;
+      cp_async_elem(dst + idx, ut + (size_t)wrap_index(y0 - R + row, H) * W + x);
+    }
+    cp_async_commit();
+  };
+  stage_u(p.steps - 1, ucur);
   for (int i = tid; i < (p.N + 1) * KK; i += blockDim.x) taps[i] = i < KK ? p.k0[i] : p.kernels[i - KK];
   __syncthreads();
   build_combined_stencil<T, K>(p, taps, w, y0, hb);
-  const size_t img = (size_t)H * W, stride = (size_t)p.B * img;
   // adjoint of the last state = its seed
   const T *seed_last = p.grad_states + (p.grad_all ? (size_t)(p.steps - 1) * stride : 0) + (size_t)b * img;
   for (int idx = tid; idx < hb * W; idx += blockDim.x) lam0[R * W + idx] = seed_last[(size_t)y0 * W + idx];
   cluster.sync();
   fetch_halo<T, K>(cluster, lam0, hb, W, H, cs, rank);
+  cp_async_wait<0>();
   __syncthreads();
 
   int py[PTS], px[PTS], xm[PTS][K];
@@ -226,15 +253,15 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_bwd_kern
 #pragma unroll
     for (int e = 0; e < KK; ++e) Racc[q][e] = T(0);
   }
+  // adjoint halos are pushed into the ring neighbours' buffers as in the forward kernel: one cluster barrier per step
+  const int up = (rank + cs - 1) % cs, dn = (rank + 1) % cs;
+  const int hb_up = band_start(up + 1, H, cs) - band_start(up, H, cs);
   T *cur = lam0, *nxt = lam1;
+  T *nxt_up = cluster.map_shared_rank(lam1, up), *cur_up = cluster.map_shared_rank(lam0, up);
+  T *nxt_dn = cluster.map_shared_rank(lam1, dn), *cur_dn = cluster.map_shared_rank(lam0, dn);
   for (int t = p.steps - 1; t >= 0; --t) {
-    // stage u_t (band + halo rows, wrapped) from global memory
-    const T *ut = (t == 0 ? p.u0 : p.states + (size_t)(t - 1) * stride) + (size_t)b * img;
-    for (int idx = tid; idx < (hb + 2 * R) * W; idx += blockDim.x) {
-      const int row = idx / W, x = idx - row * W;
-      ubuf[idx] = ut[(size_t)wrap_index(y0 - R + row, H) * W + x];
-    }
-    __syncthreads();
+    if (t > 0) stage_u(t - 1, unxt); // `unxt` was read last during step t + 1, before the barrier that ended it
+    const T *ubuf = ucur;
     const T *inj = (p.grad_all && t > 0) ? p.grad_states + (size_t)(t - 1) * stride + (size_t)b * img + (size_t)y0 * W
                                          : nullptr;
     T *gu = (t == 0 && p.grad_u0) ? p.grad_u0 + (size_t)b * img + (size_t)y0 * W : nullptr;
@@ -266,14 +293,20 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_bwd_kern
       }
       if (inj) acc += inj[py[q] * W + px[q]];
       nxt[(R + py[q]) * W + px[q]] = acc;
+      if (t > 0) {
+        if (py[q] < R) nxt_up[(R + hb_up + py[q]) * W + px[q]] = acc;
+        if (py[q] >= hb - R) nxt_dn[(py[q] - (hb - R)) * W + px[q]] = acc;
+      }
       if (gu) gu[py[q] * W + px[q]] = acc;
     }
+    cp_async_wait<0>(); // this thread's share of u_{t-1} has landed; the barrier publishes everybody's
     cluster.sync();
-    if (t > 0) fetch_halo<T, K>(cluster, nxt, hb, W, H, cs, rank);
-    __syncthreads();
     T *tmp = cur;
     cur = nxt;
     nxt = tmp;
+    tmp = cur_up, cur_up = nxt_up, nxt_up = tmp;
+    tmp = cur_dn, cur_dn = nxt_dn, nxt_dn = tmp;
+    tmp = ucur, ucur = unxt, unxt = tmp;
   }
   // tap correlations of this trajectory's band
   T *Rb = p.R + (size_t)b * KK * img + (size_t)y0 * W;
@@ -283,29 +316,48 @@ __global__ void __launch_bounds__(kLinClusterThreads, 1) linear_cluster_bwd_kern
 #pragma unroll
       for (int e = 0; e < KK; ++e) Rb[(size_t)e * img + py[q] * W + px[q]] = Racc[q][e];
     }
-  cluster.sync();
 }
 
 // ---- finishing kernels: parameter gradients from the tap correlations (fixed order: deterministic) ---------
 // Rsum[e][p] = sum_b R[b][e][p];  grad_coe[n][p] = dt * sum_e K_n[e] * Rsum[e][p]
+// A block owns kDcoePts consecutive points: first one thread per (tap e, point) sums over the batch in order (the B
+// loads of a thread are independent, the points of a tap contiguous), the sums stay in shared memory in double;
+// then one thread per (field n, point) combines the KK taps in order.  (The first version ran ONE thread per point
+// through all KK*B loads and N*KK multiply-adds: 2500 threads on the whole GPU at BASELINE config 2, 69 us -- the
+// third-longest kernel of that pass.  Same addends in the same order: bit-identical.)
+constexpr int kDcoePts = 16, kDcoeThreads = 256;
 template <typename T>
-__global__ void lin_cluster_dcoe_kernel(const T *R, int B, int KK, size_t img, const T *kernels, int N, T dt, T *Rsum,
-                                        T *grad_coe) {
-  const size_t pidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pidx >= img) return;
-  double rs[PDENET_MAX_K * PDENET_MAX_K];
-  for (int e = 0; e < KK; ++e) {
-    double s = 0.0;
-    for (int b = 0; b < B; ++b) s += (double)R[((size_t)b * KK + e) * img + pidx];
-    rs[e] = s;
-    Rsum[(size_t)e * img + pidx] = (T)s;
-  }
+__global__ void __launch_bounds__(kDcoeThreads) lin_cluster_dcoe_kernel(const T *R, int B, int KK, size_t img,
+                                                                        const T *kernels, int N, T dt, T *Rsum,
+                                                                        T *grad_coe) {
+  __shared__ double rs[PDENET_MAX_K * PDENET_MAX_K][kDcoePts];
+  __shared__ double kw[PDENET_MAX_FILTERS * PDENET_MAX_K * PDENET_MAX_K];
+  const size_t p0 = (size_t)blockIdx.x * kDcoePts;
   if (grad_coe)
-    for (int n = 0; n < N; ++n) {
-      double s = 0.0;
-      for (int e = 0; e < KK; ++e) s += (double)kernels[n * KK + e] * rs[e];
-      grad_coe[(size_t)n * img + pidx] = (T)((double)dt * s);
+    for (int i = threadIdx.x; i < N * KK; i += kDcoeThreads) kw[i] = (double)kernels[i];
+  for (int i = threadIdx.x; i < KK * kDcoePts; i += kDcoeThreads) {
+    const int e = i / kDcoePts, q = i % kDcoePts;
+    const size_t pidx = p0 + q;
+    double s = 0.0;
+    if (pidx < img) {
+      const T *r = R + (size_t)e * img + pidx;
+      const size_t bstride = (size_t)KK * img;
+#pragma unroll 8
+      for (int b = 0; b < B; ++b) s += (double)r[(size_t)b * bstride];
+      Rsum[(size_t)e * img + pidx] = (T)s;
     }
+    rs[e][q] = s;
+  }
+  if (!grad_coe) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N * kDcoePts; i += kDcoeThreads) {
+    const int n = i / kDcoePts, q = i % kDcoePts;
+    const size_t pidx = p0 + q;
+    if (pidx >= img) continue;
+    double s = 0.0;
+    for (int e = 0; e < KK; ++e) s += kw[n * KK + e] * rs[e][q];
+    grad_coe[(size_t)n * img + pidx] = (T)((double)dt * s);
+  }
 }
 // constant coefficients: grad_coe[n] = sum_p field_grad[n][p]  (one block per n, fixed order)
 template <typename T> __global__ void __launch_bounds__(256) lin_cluster_dcoe_const_kernel(const T *field, size_t img, T *out) {
