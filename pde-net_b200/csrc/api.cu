@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <mutex>
 #include <vector>
 
@@ -934,7 +936,7 @@ static int rollout_bwd(const T *u0, const T *states, const T *feats, const T *gr
 
 // ---- PDE-Net 1 linear rollout (row a12) ------------------------------------------------------
 // Small grids: one trajectory per thread-block cluster, resident in shared memory over all steps
-// (linear_cluster_kernels.cuh).  lin_cluster_plan returns the CTAs per cluster (1, 2, 4 or 8) or 0 when the
+// (linear_cluster_kernels.cuh).  lin_cluster_plan returns the CTAs per cluster (1 .. 8) or 0 when the
 // grid does not fit (then the tiled kernels run).
 static std::atomic<int> g_linear_cluster_on{1};
 
@@ -942,12 +944,70 @@ struct LinClusterPlan {
   int cs, pts, hb_max;
   size_t smem;
 };
-static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, int N, int sms) {
+// Clusters of `cs` CTAs of the given kernel that the device holds at once (cudaOccupancyMaxActiveClusters: the
+// CTAs of a cluster must share a GPC, so e.g. only 15 clusters of 8 fit a B200 although 15 * 8 < 148), or 0 if the
+// query fails.  Cached per (scalar size, k, points per thread, direction, cluster size, shared memory).
+template <typename KernelT> static int query_active_clusters(KernelT kern, int cs, size_t smem) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cs);
+  cfg.blockDim = dim3(kLinClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+template <typename T> static int active_clusters_t(int k, int pts, int bwd, int cs, size_t smem) {
+#define PDENET_OCC(KK_, PTS_)                                                                                     \
+  if (k == KK_ && pts == PTS_)                                                                                    \
+    return bwd ? query_active_clusters(linear_cluster_bwd_kernel<T, KK_, PTS_>, cs, smem)                         \
+               : query_active_clusters(linear_cluster_fwd_kernel<T, KK_, PTS_>, cs, smem);
+  PDENET_OCC(3, 1) PDENET_OCC(3, 2) PDENET_OCC(5, 1) PDENET_OCC(5, 2) PDENET_OCC(7, 1)
+#undef PDENET_OCC
+  return 0;
+}
+static int active_clusters(size_t es, int k, int pts, int bwd, int cs, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<size_t, int, int, int, int, size_t, int>, int> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const auto key = std::make_tuple(es, k, pts, bwd, cs, smem, dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int n = es == 8 ? active_clusters_t<double>(k, pts, bwd, cs, smem) : active_clusters_t<float>(k, pts, bwd, cs, smem);
+  cache[key] = n;
+  return n;
+}
+
+// Cluster size (1..8 CTAs per trajectory, any integer: bands need not be equal) for the small-grid path.  Every size
+// whose band fits a CTA (<= 256 * pts points, <= 220 KB, at least r rows) is a candidate; the choice minimises
+//   waves * (2 + points per thread),   waves = ceil(B / clusters the device holds at once),
+// a model of a launch that is all latency (per step: one cluster barrier + one dependent tap chain per point of a
+// thread), ties to the larger cluster.  BASELINE config 2 (B = 16, 50 x 50, 5 x 5): clusters of 8 run as TWO waves
+// (15 resident + 1 straggler: measured 81 us forward, the SMs active for 40 of them), clusters of 7 as one.
+static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, int N, int sms, int bwd = 0) {
   LinClusterPlan none = {0, 0, 0, 0};
   if (!g_linear_cluster_on.load(std::memory_order_relaxed) || (k != 3 && k != 5 && k != 7)) return none;
   const int r = (k - 1) / 2, kk = k * k, pts_max = k == 7 ? 1 : 2;
   auto fits = [&](int cs, LinClusterPlan &pl) {
-    if (H / cs < r || H / cs < 1) return false; // every band must own the halo rows its neighbours fetch
+    if (H / cs < r || H / cs < 1) return false; // every band must own the halo rows its neighbours need
     const int hb_max = (H + cs - 1) / cs;
     if ((long long)hb_max * W > (long long)kLinClusterThreads * pts_max) return false;
     const size_t elems = (size_t)(N + 1) * kk + (size_t)(hb_max + 2 * r) * kk * W + 4 * (size_t)(hb_max + 2 * r) * W;
@@ -959,10 +1019,16 @@ static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, in
     return true;
   };
   LinClusterPlan best = none, cand;
-  for (int cs = 1; cs <= 8; cs *= 2)
+  long long best_cost = 0;
+  for (int cs = 1; cs <= 8; ++cs)
     if (fits(cs, cand)) {
-      if (!best.cs) best = cand;                                  // smallest cluster that fits ...
-      else if ((long long)B * cs <= sms) best = cand;             // ... widened while SMs would otherwise idle
+      int n = active_clusters(es, k, cand.pts, bwd, cs, cand.smem);
+      if (n <= 0) n = sms / cs > 0 ? sms / cs : 1; // no device / query failed: one CTA per SM, GPC limits ignored
+      const long long waves = ((long long)B + n - 1) / n, cost = waves * (2 + cand.pts);
+      if (!best.cs || cost <= best_cost) {
+        best = cand;
+        best_cost = cost;
+      }
     }
   return best;
 }
@@ -1101,7 +1167,7 @@ static int linear_bwd(const T *u0, const T *states, const T *grad_states, int gr
   const size_t img = (size_t)H * W;
   const size_t stride = (size_t)B * img;
   {
-    const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms);
+    const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms, 1);
     if (pl.cs) { // small grid: reverse rollout in one launch + two finishing kernels
       const int kk = k * k;
       LinClusterParams<T> q;
@@ -1351,7 +1417,7 @@ static int snl_bwd(const T *u0, const T *states, const T *grad_states, int grad_
   if (degree < 1 || degree > 4) return PDENET_E_UNSUPPORTED;
   const int sms = sm_count();
   if (sms <= 0) return PDENET_E_CUDA;
-  const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms);
+  const LinClusterPlan pl = lin_cluster_plan(sizeof(T), B, H, W, k, N, sms, 1);
   if (!pl.cs) return PDENET_E_UNSUPPORTED;
   const SnlLayout lay = snl_layout(sizeof(T), B, H, W, k, N, steps, mesh, degree, sms);
   if (ws_bytes < lay.total) return PDENET_E_WORKSPACE;

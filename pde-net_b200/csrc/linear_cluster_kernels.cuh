@@ -93,11 +93,20 @@ __device__ __forceinline__ void build_combined_stencil(const LinClusterParams<T>
     T acc[KK];
 #pragma unroll
     for (int e = 0; e < KK; ++e) acc[e] = T(0);
-    for (int n = 0; n < N; ++n) {
-      const T c = p.coe_const ? p.coe[n] : p.coe[((size_t)n * H + g) * W + x];
-      const T *kn = taps + (n + 1) * KK;
+    // all coefficient loads of the point first (independent, in flight together), then the multiply-adds in filter
+    // order: a run-time loop with the load at its top paid one global-memory round trip per filter and point -- ~40 of
+    // the 80 us of a BASELINE config-2 forward launch were this prologue
+    T cv[kMaxFilters];
 #pragma unroll
-      for (int e = 0; e < KK; ++e) acc[e] = fma_(c, kn[e], acc[e]);
+    for (int n = 0; n < kMaxFilters; ++n)
+      cv[n] = n < N ? (p.coe_const ? p.coe[n] : p.coe[((size_t)n * H + g) * W + x]) : T(0);
+#pragma unroll
+    for (int n = 0; n < kMaxFilters; ++n) {
+      if (n < N) {
+        const T *kn = taps + (n + 1) * KK;
+#pragma unroll
+        for (int e = 0; e < KK; ++e) acc[e] = fma_(cv[n], kn[e], acc[e]);
+      }
     }
 #pragma unroll
     for (int e = 0; e < KK; ++e) w[((size_t)row * KK + e) * W + x] = fma_(p.dt, acc[e], taps[e]);
