@@ -392,6 +392,11 @@ PDENET_API int pdenet_single_nonlinear_rollout_bwd_f32(const float *u0, const fl
  * Results are identical bit for bit (same per-point arithmetic; the partial sums of the parameter gradients are
  * grouped differently, fixed order either way).  Returns the previous factor; a negative argument only queries. */
 PDENET_API int pdenet_small_tile_factor(int factor);
+/* The filter-gradient kernel also has a MEDIUM tile (64 x 32 points), taken when a launch has too few large tiles
+ * but at least `factor` medium ones per CTA slot (BASELINE config 3).  pdenet_filter_grad_tile_level(level) forces
+ * its tile for periodic launches: 0 large, 1 small, 2 medium, -1 back to the policy (process-global; returns the
+ * previous setting; other values only query): testing / measurement aid. */
+PDENET_API int pdenet_filter_grad_tile_level(int level);
 
 /* ---- measurement hooks (bench.py; not part of the reference interface) ------------------------
  * Kernel kinds: 0 = fused forward step, 1 = reverse kernel A (stencils + SymNet reverse),

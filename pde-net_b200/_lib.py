@@ -53,6 +53,7 @@ _PROTOS = {
     "pdenet_single_nonlinear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 10 + [_sz] + [_i] * 6
                                                 + [_d, _d, _d, _i, _i, _vp]),
     "pdenet_small_tile_factor": (_i, [_i]),
+    "pdenet_filter_grad_tile_level": (_i, [_i]),
     "pdenet_linear_rollout_bwd_workspace_bytes": (_sz, [_i] * 6),
     "pdenet_linear_rollout_bwd_{t}": (_i, [_vp, _vp, _vp, _i] + [_vp] * 8 + [_sz] + [_i] * 6 + [_d, _vp]),
     "pdenet_slab_step_fwd_{t}": (_i, [_vp] * 4 + [_i] * 10 + [_d, _vp]),

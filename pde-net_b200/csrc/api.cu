@@ -24,6 +24,8 @@ static std::atomic<int> g_small_tile_factor{[] {
   return e ? atoi(e) : 4;
 }()};
 int small_tile_factor() { return g_small_tile_factor.load(std::memory_order_relaxed); }
+static std::atomic<int> g_fgrad_level{-1};
+int filter_grad_tile_level() { return g_fgrad_level.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 // measurement hooks: launch counters (always) + per-launch event pairs (when enabled)
@@ -472,8 +474,15 @@ static int run_filter_grad(FGradParams<T> &p, int B, int C, int N, int H, int W,
   p.H = H;
   p.W = W;
   const long long big_items = (long long)B * C * ((W + tw - 1) / tw) * ((H + th - 1) / th);
-  const int small = p.wrap_y && big_items < (long long)small_tile_factor() * sms * kFGradCtasPerSm;
-  if (small) filter_grad_tile<T, K>(1, tw, th);
+  const long long enough = (long long)small_tile_factor() * sms * kFGradCtasPerSm;
+  int small = 0; // tile level: 0 large, 2 medium, 1 small -- the largest tile that still gives `enough` items
+  if (p.wrap_y && big_items < enough) {
+    filter_grad_tile<T, K>(2, tw, th);
+    const long long med_items = (long long)B * C * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+    small = med_items >= enough ? 2 : 1;
+  }
+  if (p.wrap_y && filter_grad_tile_level() >= 0) small = filter_grad_tile_level();
+  filter_grad_tile<T, K>(small, tw, th);
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.n_items = B * C * p.tiles_x * p.tiles_y;
@@ -2084,6 +2093,11 @@ int pdenet_small_tile_factor(int factor) {
   return g_small_tile_factor.exchange(factor);
 }
 
+int pdenet_filter_grad_tile_level(int level) {
+  const int prev = pdenet::g_fgrad_level.load(std::memory_order_relaxed);
+  if (level >= -1 && level <= 2) pdenet::g_fgrad_level.store(level, std::memory_order_relaxed);
+  return prev;
+}
 int pdenet_linear_small_grid_path(int on) {
   const int prev = g_linear_cluster_on.exchange(on != 0 ? 1 : 0);
   return prev;

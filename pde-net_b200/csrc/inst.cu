@@ -20,7 +20,8 @@ constexpr size_t kMaxDynamicSmem = 227 * 1024;
 
 template <typename T, int K, int N, int C, int MODE, int VL, int LT = -1, int NTO = 0>
 static int launch_step_one(const StepParams<T> &p_in, int sms, cudaStream_t st) {
-  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N)>;
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N),
+                      step_spw_override(MODE)>;
   StepParams<T> p = p_in;
   p.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
   p.tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
@@ -154,12 +155,14 @@ template <typename T, int K, int MT_> static int launch_filter_grad_v(const FGra
   kern<<<grid, Cfg::NT, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
+// `small`: 0 = large tile (kFGradMT micro-tiles of 8 rows), 1 = small (16 rows), 2 = medium (kFGradMediumMT: 32 rows)
 template <typename T, int K> int launch_filter_grad(const FGradParams<T> &p, int grid, int small, cudaStream_t st) {
+  if (small == 2) return launch_filter_grad_v<T, K, kFGradMediumMT>(p, grid, st);
   return small ? launch_filter_grad_v<T, K, 2>(p, grid, st) : launch_filter_grad_v<T, K, kFGradMT>(p, grid, st);
 }
 template <typename T, int K> void filter_grad_tile(int small, int &tw, int &th) {
   tw = FGradCfg<T, K>::TW;
-  th = small ? FGradCfg<T, K, 2>::TH : FGradCfg<T, K, kFGradMT>::TH;
+  th = small == 2 ? FGradCfg<T, K, kFGradMediumMT>::TH : (small ? FGradCfg<T, K, 2>::TH : FGradCfg<T, K, kFGradMT>::TH);
 }
 
 template <typename T, int K> int upload_taps(int slot, int first, const T *taps, int n_filters, cudaStream_t st) {

@@ -126,6 +126,12 @@ constexpr int kAdjNT = PDENET_B1_NT;
 #endif
 constexpr int kFGradWarps = PDENET_B2_WARPS;
 constexpr int kFGradMT = PDENET_B2_MT;
+// medium tile (32 rows) for launches with too few large tiles but plenty of medium ones (BASELINE config 3: 256 large
+// items on 148 CTAs are 1.7 waves; 2048 small items balance but pay 1.4x the halo staging; 1024 medium items: B2
+// 74 -> 66 us per launch there)
+constexpr int kFGradMediumMT = 4;
+// forced tile level of the filter-gradient kernel (-1 = by the policy above; pdenet_filter_grad_tile_level())
+int filter_grad_tile_level();
 constexpr int kFGradCtasPerSm = kFGradWarps <= 6 ? 2 : 1;
 
 template <typename T> struct FGradParams {

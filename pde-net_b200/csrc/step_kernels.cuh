@@ -24,7 +24,13 @@ template <typename T> struct TransposeCfg {
 #ifndef PDENET_STEP_SPW
 #define PDENET_STEP_SPW 2   // strips per warp and large tile
 #endif
-template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0> struct StepCfg {
+#ifndef PDENET_STEP_SPW_KEPT
+#define PDENET_STEP_SPW_KEPT 1   // ... of kernel A on kept features: it stages no tile (no halo to amortise), and 64 x 16-point
+                                 // items measured 4-5 % faster than 64 x 32 (1.595 -> 1.52 ms per 32 trajectories, cfg4 fp64)
+#endif
+// strips per warp of a mode's large tile (0 = PDENET_STEP_SPW)
+__host__ __device__ constexpr int step_spw_override(int mode) { return mode_is_kept(mode) ? PDENET_STEP_SPW_KEPT : 0; }
+template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0, int SPWO = 0> struct StepCfg {
   static constexpr int R = (K - 1) / 2;
   static constexpr int NT = NT_;
   // points per thread strip: 4 in fp64; 8 in fp32 (FFMA issues every cycle, so each uniform tap
@@ -35,7 +41,7 @@ template <typename T, int K, int N, int C, int NT_ = 256, int PO = 0> struct Ste
   // warp layout of a tile: WA warps across (32 columns each), WD down, SPW strips of P rows per warp.
   // NT >= 256: the large tile, 64 x (NT/64 * 2P).  NT == 128: the SMALL tile, 32 x 4P (four warps stacked),
   // for problems whose large-tile count would leave SMs idle or badly balanced (BASELINE configs 1 and 3).
-  static constexpr int WA = NT >= 256 ? 2 : 1, WD = NT / 32 / WA, SPW = NT >= 256 ? PDENET_STEP_SPW : 1;
+  static constexpr int WA = NT >= 256 ? 2 : 1, WD = NT / 32 / WA, SPW = NT >= 256 ? (SPWO ? SPWO : PDENET_STEP_SPW) : 1;
   static constexpr int TW = 32 * WA, TH = WD * SPW * P;
   static constexpr int SR = TH + K - 1, SC = TW + K - 1;
   static constexpr int PITCH = SC;
@@ -672,7 +678,8 @@ __device__ __forceinline__ void upwind_reverse_half(T (&d)[MD][P], const T *syms
 template <typename T, int K, int N, int C, int MODE, int VL, int LT, int NTO = 0>
 __global__ void __launch_bounds__(NTO ? NTO : step_threads_t<T>(MODE, C *N), NTO ? 2 : step_min_blocks<T>(MODE, C *N))
     step_kernel(const StepParams<T> p) {
-  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N)>;
+  using Cfg = StepCfg<T, K, N, C, (NTO ? NTO : step_threads_t<T>(MODE, C * N)), step_p_override<T>(MODE, C * N),
+                      step_spw_override(MODE)>;
   constexpr int R = Cfg::R, TW = Cfg::TW, TH = Cfg::TH, P = Cfg::P, SR = Cfg::SR, SC = Cfg::SC;
   constexpr int PITCH = Cfg::PITCH, M = Cfg::M, NT = Cfg::NT;
   constexpr bool LINEAR = (MODE == MODE_LIN_FWD || MODE == MODE_LIN_BWD_A);
