@@ -185,7 +185,8 @@ PDENET_API int pdenet_rhs_upwind_bwd_f32(const float *u, const float *grad_out, 
                               size_t workspace_bytes, int batch_chunk, int B, int C, int H, int W, int k, int N, int L,
                               void *stream);
 
-/* Feature-keeping variant of the rollout (same results, bit for bit; trades HBM for FP64 work).
+/* Feature-keeping variant of the rollout (same states, input and filter gradients, bit for bit; the SymNet gradient
+ * equal up to the order of its sum over the points, ~1e-15 relative in fp64; trades HBM for FP64 work).
  * pdenet_rollout_fwd_keep_* additionally stores the C*N derivative features of every step's
  * INPUT state: feats[t] = FD bank applied to u_t, t = 0..steps-1, layout [steps][B][C*N][H][W]
  * (what the reference's autograd keeps alive as conv2d outputs, polypde.py::UInputs [RECALL]).
