@@ -220,8 +220,8 @@ PDENET_API int pdenet_linear_rollout_fwd_f32(const float *u0, const float *id_ke
                                   void *stream);
 /* Small grids (a band of the grid per CTA fits in shared memory; BASELINE config 2: 50 x 50) take a dedicated
  * path: ONE launch per direction, one trajectory per thread-block cluster (1-8 CTAs), state / adjoint resident
- * in shared memory over all steps, halo rows read from the neighbour CTAs' shared memory, one cluster barrier
- * per step; the N+1 filters and coefficient fields are folded into one variable-coefficient stencil per point
+ * in shared memory over all steps, halo rows stored straight into the neighbour CTAs' shared memory, one cluster
+ * barrier per step, cluster size chosen by what the device can hold at once (cudaOccupancyMaxActiveClusters); the N+1 filters and coefficient fields are folded into one variable-coefficient stencil per point
  * (exact, they are constant over a rollout).  Same results up to re-association.
  * pdenet_linear_small_grid_path(0) switches it off (process-global; returns the previous setting): testing /
  * measurement aid, the tiled kernels then serve every size. */

@@ -1010,7 +1010,8 @@ static int active_clusters(size_t es, int k, int pts, int bwd, int cs, size_t sm
 //   waves * (2 + points per thread),   waves = ceil(B / clusters the device holds at once),
 // a model of a launch that is all latency (per step: one cluster barrier + one dependent tap chain per point of a
 // thread), ties to the larger cluster.  BASELINE config 2 (B = 16, 50 x 50, 5 x 5): clusters of 8 run as TWO waves
-// (15 resident + 1 straggler: measured 81 us forward, the SMs active for 40 of them), clusters of 7 as one.
+// (15 resident + 1 straggler: measured 81 us forward, the SMs active for 40 of them; 7 do not all fit either),
+// clusters of 6 as one (49 us).
 static LinClusterPlan lin_cluster_plan(size_t es, int B, int H, int W, int k, int N, int sms, int bwd = 0) {
   LinClusterPlan none = {0, 0, 0, 0};
   if (!g_linear_cluster_on.load(std::memory_order_relaxed) || (k != 3 && k != 5 && k != 7)) return none;
