@@ -351,3 +351,53 @@ def test_upwind_torch_oracle_matches_numpy_adjoint(k, C, L):
     assert rel(lv[2].grad.numpy(), dsym) < 1e-12
     # and the scheme really differs from the central one for these one-sided filters
     assert (out.detach() - O.rollout(u0, Ks, sym, L, dt, steps)[-1]).abs().max() > 1e-6
+
+
+def test_linear_model_combined_stencil_and_tap_correlation_identities():
+    """The algebra the small-grid CUDA path of the PDE-Net 1 linear model rests on (DESIGN.md section 3.9,
+    csrc/linear_cluster_kernels.cuh), checked on the CPU against the oracle's step and its autograd:
+    one step is ONE variable-coefficient stencil  u+(p) = sum_ab w_ab(p) u(p + ab - r),
+    w_ab(p) = K0[ab] + dt sum_n c_n(p) K_n[ab];  and with the tap correlations
+    R_ab(p) = sum_t lam_{t+1}(p) u_t(p + ab - r)  (lam = adjoint of the rollout) every parameter gradient is
+    dK0[ab] = sum_p R_ab,  dK_n[ab] = dt sum_p c_n R_ab,  dc_n(p) = dt sum_ab K_n[ab] R_ab(p)."""
+    g = torch.Generator().manual_seed(5)
+    k, N, B, H, W, steps, dt = 5, 4, 2, 9, 11, 3, 0.013
+    r = (k - 1) // 2
+    K0 = (torch.eye(k * k, dtype=torch.float64)[k * k // 2].reshape(k, k)
+          + 0.01 * torch.randn(k, k, generator=g, dtype=torch.float64)).requires_grad_(True)
+    Ks = torch.randn(N, k, k, generator=g, dtype=torch.float64).requires_grad_(True)
+    coe = torch.randn(N, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
+    u0 = torch.randn(B, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
+    wts = torch.randn(steps, B, H, W, generator=g, dtype=torch.float64)
+    states = O.linear_rollout(u0, K0, Ks, coe, dt, steps)
+    (torch.stack(states) * wts).sum().backward()
+
+    def shifted(u, a, b):  # u(p + (a, b) - r), periodic
+        return torch.roll(u, shifts=(r - a, r - b), dims=(-2, -1))
+
+    with torch.no_grad():
+        w = K0.reshape(k * k)[:, None, None] + dt * torch.einsum("nhw,ne->ehw", coe, Ks.reshape(N, k * k))  # [kk,H,W]
+        # forward: the combined stencil reproduces the oracle's states
+        u = u0.detach()
+        us = [u]
+        for t in range(steps):
+            u = sum(w[a * k + b] * shifted(u, a, b) for a in range(k) for b in range(k))
+            assert (u - states[t].detach()).abs().max() < 1e-12
+            us.append(u)
+        # reverse: lam_T = seed; lam_t(q) = seed_t(q) + sum_ab (w_ab lam_{t+1})(q - ab + r)
+        lam = wts[steps - 1].clone()
+        R = torch.zeros(k * k, B, H, W, dtype=torch.float64)
+        for t in range(steps - 1, -1, -1):
+            for a in range(k):
+                for b in range(k):
+                    R[a * k + b] += lam * shifted(us[t], a, b)
+            nxt = sum(torch.roll(w[a * k + b] * lam, shifts=(a - r, b - r), dims=(-2, -1))
+                      for a in range(k) for b in range(k))
+            lam = nxt + (wts[t - 1] if t > 0 else 0)
+        assert (lam - u0.grad).abs().max() < 1e-11 * u0.grad.abs().max()
+        Rsum = R.sum(dim=1)                                                   # [kk,H,W], summed over the batch
+        dK0 = Rsum.sum(dim=(1, 2)).reshape(k, k)
+        dKs = dt * torch.einsum("nhw,ehw->ne", coe, Rsum).reshape(N, k, k)
+        dcoe = dt * torch.einsum("ne,ehw->nhw", Ks.reshape(N, k * k), Rsum)
+    for got, ref in ((dK0, K0.grad), (dKs, Ks.grad), (dcoe, coe.grad)):
+        assert (got - ref).abs().max() < 1e-11 * ref.abs().max()
